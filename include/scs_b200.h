@@ -1,0 +1,255 @@
+/*
+ * scs_b200.h -- C ABI of libscsb200.so, the B200-native (sm_100a) backend for the SCS
+ * ADMM iteration.  Plain pointers and sizes only: no torch / CUDA types cross this line.
+ *
+ * Three groups of entry points, each citing the reference interface it replaces
+ * ("S/" = /root/reference/scs_source/):
+ *
+ *  (1) the public SCS C API   (S/include/scs.h:271-338)  -- device-resident ADMM loop;
+ *      this is what scs/scspy.c + scs/scsobject.h bind (scsobject.h:520,903,986,1217,1240).
+ *  (2) the ScsLinSysWork plugin ABI (S/include/linsys.h:25-71) with the reference's
+ *      host-pointer semantics, so the reference core (scs.c compiled with -DINDIRECT=1)
+ *      can link this library as its linear-system backend unchanged.
+ *  (3) scs_b200_* : device-resident replacements of the reference's internal host helpers
+ *      that its C tests link against (SCS(proj_dual_cone) cones.c:1544, SCS(accum_by_*)
+ *      scs_matrix.c:135-199, aa_apply/aa_safeguard aa.c:822-901), exposed with host
+ *      buffers for parity tests, plus batch / multi-GPU and measurement hooks that have
+ *      no reference counterpart.
+ *
+ * Struct layouts below are bit-identical to the reference's non-DLONG, non-SFLOAT,
+ * non-USE_SPECTRAL_CONES build (scs_types.h:14-33; GPU builds force 32-bit ints,
+ * meson.build:169-174).
+ */
+#ifndef SCS_B200_H_GUARD
+#define SCS_B200_H_GUARD
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int scs_int;      /* S/include/scs_types.h:14-25 (DLONG off) */
+typedef double scs_float; /* S/include/scs_types.h:27-33 (SFLOAT off) */
+
+/* exit flags, S/include/scs.h:33-42 */
+#define SCS_INFEASIBLE_INACCURATE (-7)
+#define SCS_UNBOUNDED_INACCURATE (-6)
+#define SCS_SIGINT (-5)
+#define SCS_FAILED (-4)
+#define SCS_INDETERMINATE (-3)
+#define SCS_INFEASIBLE (-2)
+#define SCS_UNBOUNDED (-1)
+#define SCS_UNFINISHED (0)
+#define SCS_SOLVED (1)
+#define SCS_SOLVED_INACCURATE (2)
+
+/* S/include/aa_stats.h:21-42 */
+typedef struct {
+  scs_int iter;
+  scs_int n_accept;
+  scs_int n_reject_lapack;
+  scs_int n_reject_rank0;
+  scs_int n_reject_nonfinite;
+  scs_int n_reject_weight_cap;
+  scs_int n_safeguard_reject;
+  scs_int last_rank;
+  scs_float last_aa_norm;
+  scs_float last_regularization;
+} AaStats;
+
+/* CSC matrix, S/include/scs.h:47-58 */
+typedef struct {
+  scs_float *x;
+  scs_int *i;
+  scs_int *p;
+  scs_int m;
+  scs_int n;
+} ScsMatrix;
+
+/* S/include/scs.h:61-101 */
+typedef struct {
+  scs_int normalize;
+  scs_float scale;
+  scs_int adaptive_scale;
+  scs_float rho_x;
+  scs_int max_iters;
+  scs_float eps_abs;
+  scs_float eps_rel;
+  scs_float eps_infeas;
+  scs_float alpha;
+  scs_float time_limit_secs;
+  scs_int verbose;
+  scs_int warm_start;
+  scs_int acceleration_lookback;
+  scs_int acceleration_interval;
+  scs_int acceleration_type_1;
+  scs_float acceleration_regularization;
+  scs_float acceleration_relaxation;
+  const char *write_data_filename; /* accepted, ignored by this backend (rw.c out of scope) */
+  const char *log_csv_filename;    /* accepted, ignored by this backend (rw.c out of scope) */
+} ScsSettings;
+
+/* S/include/scs.h:104-119 */
+typedef struct {
+  scs_int m;
+  scs_int n;
+  ScsMatrix *A; /* m x n CSC, row indices sorted within a column */
+  ScsMatrix *P; /* n x n upper-triangular CSC, or NULL */
+  scs_float *b;
+  scs_float *c;
+} ScsData;
+
+/* S/include/scs.h:122-173 (spectral cones compiled out) */
+typedef struct {
+  scs_int z;
+  scs_int l;
+  scs_float *bu;
+  scs_float *bl;
+  scs_int bsize;
+  scs_int *q;
+  scs_int qsize;
+  scs_int *s;
+  scs_int ssize;
+  scs_int *cs;
+  scs_int cssize;
+  scs_int ep;
+  scs_int ed;
+  scs_float *p;
+  scs_int psize;
+} ScsCone;
+
+/* S/include/scs.h:181-188 */
+typedef struct {
+  scs_float *x;
+  scs_float *y;
+  scs_float *s;
+} ScsSolution;
+
+/* S/include/scs.h:191-244 */
+typedef struct {
+  scs_int iter;
+  char status[128];
+  char lin_sys_solver[128];
+  scs_int status_val;
+  scs_int scale_updates;
+  scs_float pobj;
+  scs_float dobj;
+  scs_float res_pri;
+  scs_float res_dual;
+  scs_float gap;
+  scs_float res_infeas;
+  scs_float res_unbdd_a;
+  scs_float res_unbdd_p;
+  scs_float setup_time; /* milliseconds */
+  scs_float solve_time; /* milliseconds */
+  scs_float scale;
+  scs_float comp_slack;
+  scs_int rejected_accel_steps;
+  scs_int accepted_accel_steps;
+  AaStats aa_stats;
+  scs_float lin_sys_time; /* milliseconds, CUDA events */
+  scs_float cone_time;    /* milliseconds, CUDA events */
+  scs_float accel_time;   /* milliseconds, CUDA events */
+} ScsInfo;
+
+typedef struct SCS_WORK ScsWork;                /* opaque, S/include/scs.h:30 */
+typedef struct SCS_LIN_SYS_WORK ScsLinSysWork;  /* opaque, S/include/scs.h:28 */
+
+/* ---------------------------------------------------------------------------------- */
+/* (1) public SCS API -- S/include/scs.h:271-338.  Same names, arguments, ownership   */
+/*     (inputs deep-copied, scs.h:253-255) and error behaviour (NULL / SCS_FAILED with */
+/*     NaN-filled outputs, scs.c:316-359) as the reference.                            */
+/* ---------------------------------------------------------------------------------- */
+ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs); /* scs.h:271 */
+scs_int scs_update(ScsWork *w, scs_float *b, scs_float *c);                     /* scs.h:285 */
+scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info,
+                  scs_int warm_start);                                          /* scs.h:300 */
+void scs_finish(ScsWork *w);                                                    /* scs.h:308 */
+scs_int scs(const ScsData *d, const ScsCone *k, const ScsSettings *stgs,
+            ScsSolution *sol, ScsInfo *info);                                   /* scs.h:323 */
+void scs_set_default_settings(ScsSettings *stgs);                               /* scs.h:331 */
+const char *scs_version(void);                                                  /* scs.h:338 */
+
+/* ---------------------------------------------------------------------------------- */
+/* (2) linear-system plugin ABI -- S/include/linsys.h:25-71.  Host pointers in and     */
+/*     out (H2D/D2H inside the call); A, P, diag_r are copied, never retained.         */
+/* ---------------------------------------------------------------------------------- */
+ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
+                                     const scs_float *diag_r);                  /* linsys.h:25 */
+void scs_free_lin_sys_work(ScsLinSysWork *w);                                   /* linsys.h:33 */
+scs_int scs_solve_lin_sys(ScsLinSysWork *w, scs_float *b, const scs_float *s,
+                          scs_float tol);                                       /* linsys.h:53 */
+scs_int scs_update_lin_sys_diag_r(ScsLinSysWork *w,
+                                  const scs_float *new_diag_r);                 /* linsys.h:64 */
+const char *scs_get_lin_sys_method(void);                                       /* linsys.h:71 */
+/* total CG iterations so far (reference: ScsLinSysWork.tot_cg_its, cpu/indirect/private.h:28) */
+scs_int scs_b200_lin_sys_cg_its(const ScsLinSysWork *w);
+
+/* ---------------------------------------------------------------------------------- */
+/* (3) device-resident helpers with host buffers (parity-test surface)                 */
+/* ---------------------------------------------------------------------------------- */
+typedef struct SCS_B200_CONE_WORK ScsB200ConeWork;
+/* SCS(init_cone), cones.c:1490-1530 */
+ScsB200ConeWork *scs_b200_init_cone(const ScsCone *k, scs_int m);
+/* SCS(proj_dual_cone), cones.c:1544-1588: x (len m, host) <- Pi_{K*}^{R}(x).  D = scal->D
+ * (len m) or NULL, r_y (len m) or NULL.  Returns 0, <0 on failure. */
+scs_int scs_b200_proj_dual_cone(scs_float *x, ScsB200ConeWork *c, const scs_float *D,
+                                const scs_float *r_y);
+/* SCS(finish_cone), cones.c:284-338 */
+void scs_b200_finish_cone(ScsB200ConeWork *c);
+
+/* SCS(accum_by_a / accum_by_atrans / accum_by_p), scs_matrix.c:135-199: y += A x etc.
+ * A is CSC; P upper-triangular CSC.  Host buffers. Returns 0 on success. */
+scs_int scs_b200_accum_by_a(const ScsMatrix *A, const scs_float *x, scs_float *y);
+scs_int scs_b200_accum_by_atrans(const ScsMatrix *A, const scs_float *x, scs_float *y);
+scs_int scs_b200_accum_by_p(const ScsMatrix *P, const scs_float *x, scs_float *y);
+
+/* Anderson acceleration, S/include/aa.h: aa_init / aa_apply / aa_safeguard / aa_reset /
+ * aa_finish / aa_get_stats with host vectors (state S,Y,D stays in HBM). */
+typedef struct SCS_B200_AA_WORK ScsB200AaWork;
+ScsB200AaWork *scs_b200_aa_init(scs_int dim, scs_int mem, scs_int min_len, scs_int type1,
+                                scs_float regularization, scs_float relaxation,
+                                scs_float safeguard_factor, scs_float max_weight_norm,
+                                scs_int ir_max_steps);
+scs_float scs_b200_aa_apply(scs_float *f, const scs_float *x, ScsB200AaWork *a);
+scs_int scs_b200_aa_safeguard(scs_float *f_new, scs_float *x_new, ScsB200AaWork *a);
+void scs_b200_aa_reset(ScsB200AaWork *a);
+AaStats scs_b200_aa_get_stats(ScsB200AaWork *a);
+void scs_b200_aa_finish(ScsB200AaWork *a);
+
+/* ---------------------------------------------------------------------------------- */
+/* device selection, batch sharding, measurement (no reference counterpart)            */
+/* ---------------------------------------------------------------------------------- */
+/* CUDA device used by workspaces created afterwards on the calling thread (default 0). */
+scs_int scs_b200_set_device(scs_int device);
+scs_int scs_b200_device_count(void);
+
+/* Counters of one workspace since scs_init (all device work of this backend). */
+typedef struct {
+  long long kernel_launches;  /* kernels of this library launched for this workspace */
+  long long cg_iters;         /* total CG iterations */
+  long long admm_iters;       /* total ADMM iterations */
+  long long spmv_calls;       /* SpMV-type kernel launches */
+  double spmv_ms;             /* device time in SpMV kernels when timing is enabled */
+  double algorithmic_bytes;   /* SURVEY.md 8(d) byte model, accumulated per iteration */
+  long long h2d_bytes;        /* bytes copied host->device by this workspace */
+  long long d2h_bytes;        /* bytes copied device->host by this workspace */
+} ScsB200Stats;
+scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out);
+
+/* SpMV micro-benchmark used by bench.py for the roofline of the dominant kernel:
+ * which = 0: z = R_y^{-1} A p (CSR of A), 1: Gp = A' z + P p + R_x p (CSR of A', fused).
+ * Runs `reps` launches on the workspace's stream, returns average ms per launch measured
+ * with CUDA events on that stream; *alg_bytes gets the algorithmic bytes of one launch. */
+double scs_b200_bench_spmv(ScsWork *w, scs_int which, scs_int reps, double *alg_bytes);
+
+/* Solve `count` independent problems on the current device, one after another on
+ * `streams` concurrent streams (batch sharding across GPUs is done by the caller: one
+ * process per GPU, problem i -> rank i % world).  Arrays of pointers, one per problem. */
+scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, const ScsCone *const *k,
+                             const ScsSettings *stgs, ScsSolution *const *sol, ScsInfo *info,
+                             scs_int streams);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,444 @@
+"""`_scs_b200`: the per-backend extension-module surface of the reference, over libscsb200.so.
+
+The reference builds one CPython extension per linear-system backend from scs/scspy.c
+(scs/scsmodule.h, scs/scsobject.h); each exports
+
+    SCS(shape, Ax, Ai, Ap, Px, Pi, Pp, b, c, cone, **settings)   (scsobject.h:442-913)
+        .solve(warm_start, x, y, s) -> {"x","y","s","info"}       (scsobject.h:916-1130)
+        .update(b, c)                                             (scsobject.h:1133-1225)
+    version(), sizeof_int(), sizeof_float()                       (scsmodule.h:4-23)
+
+This module is that surface for the B200 backend, bound with ctypes to the C ABI declared
+in include/scs_b200.h (the same entry points scs/scspy.c binds when it is compiled with the
+PY_B200 branch shown in INTEGRATION.md).  Argument meaning, validation messages, error types,
+result keys and the per-instance lock (scsobject.h:895,939-949) follow the reference.  There
+is no CPU fallback: if libscsb200.so is missing the import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import threading
+import warnings
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libscsb200.so")
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        "scs_python_b200: %s not found. Build it with `python -m scs_python_b200.build` "
+        "(nvcc, sm_100a). This backend has no CPU fallback." % _LIB_PATH)
+lib = C.CDLL(_LIB_PATH)
+
+c_int, c_double = C.c_int, C.c_double
+p_int, p_double = C.POINTER(C.c_int), C.POINTER(C.c_double)
+
+
+class AaStats(C.Structure):
+    _fields_ = [("iter", c_int), ("n_accept", c_int), ("n_reject_lapack", c_int), ("n_reject_rank0", c_int),
+                ("n_reject_nonfinite", c_int), ("n_reject_weight_cap", c_int), ("n_safeguard_reject", c_int),
+                ("last_rank", c_int), ("last_aa_norm", c_double), ("last_regularization", c_double)]
+
+
+class ScsMatrix(C.Structure):
+    _fields_ = [("x", p_double), ("i", p_int), ("p", p_int), ("m", c_int), ("n", c_int)]
+
+
+class ScsSettings(C.Structure):
+    _fields_ = [("normalize", c_int), ("scale", c_double), ("adaptive_scale", c_int), ("rho_x", c_double),
+                ("max_iters", c_int), ("eps_abs", c_double), ("eps_rel", c_double), ("eps_infeas", c_double),
+                ("alpha", c_double), ("time_limit_secs", c_double), ("verbose", c_int), ("warm_start", c_int),
+                ("acceleration_lookback", c_int), ("acceleration_interval", c_int),
+                ("acceleration_type_1", c_int), ("acceleration_regularization", c_double),
+                ("acceleration_relaxation", c_double), ("write_data_filename", C.c_char_p),
+                ("log_csv_filename", C.c_char_p)]
+
+
+class ScsData(C.Structure):
+    _fields_ = [("m", c_int), ("n", c_int), ("A", C.POINTER(ScsMatrix)), ("P", C.POINTER(ScsMatrix)),
+                ("b", p_double), ("c", p_double)]
+
+
+class ScsCone(C.Structure):
+    _fields_ = [("z", c_int), ("l", c_int), ("bu", p_double), ("bl", p_double), ("bsize", c_int),
+                ("q", p_int), ("qsize", c_int), ("s", p_int), ("ssize", c_int), ("cs", p_int),
+                ("cssize", c_int), ("ep", c_int), ("ed", c_int), ("p", p_double), ("psize", c_int)]
+
+
+class ScsSolution(C.Structure):
+    _fields_ = [("x", p_double), ("y", p_double), ("s", p_double)]
+
+
+class ScsInfo(C.Structure):
+    _fields_ = [("iter", c_int), ("status", C.c_char * 128), ("lin_sys_solver", C.c_char * 128),
+                ("status_val", c_int), ("scale_updates", c_int), ("pobj", c_double), ("dobj", c_double),
+                ("res_pri", c_double), ("res_dual", c_double), ("gap", c_double), ("res_infeas", c_double),
+                ("res_unbdd_a", c_double), ("res_unbdd_p", c_double), ("setup_time", c_double),
+                ("solve_time", c_double), ("scale", c_double), ("comp_slack", c_double),
+                ("rejected_accel_steps", c_int), ("accepted_accel_steps", c_int), ("aa_stats", AaStats),
+                ("lin_sys_time", c_double), ("cone_time", c_double), ("accel_time", c_double)]
+
+
+class ScsB200Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_longlong), ("cg_iters", C.c_longlong), ("admm_iters", C.c_longlong),
+                ("spmv_calls", C.c_longlong), ("spmv_ms", c_double), ("algorithmic_bytes", c_double),
+                ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong)]
+
+
+# --- prototypes (include/scs_b200.h) ---
+lib.scs_init.restype = C.c_void_p
+lib.scs_init.argtypes = [C.POINTER(ScsData), C.POINTER(ScsCone), C.POINTER(ScsSettings)]
+lib.scs_update.restype = c_int
+lib.scs_update.argtypes = [C.c_void_p, p_double, p_double]
+lib.scs_solve.restype = c_int
+lib.scs_solve.argtypes = [C.c_void_p, C.POINTER(ScsSolution), C.POINTER(ScsInfo), c_int]
+lib.scs_finish.restype = None
+lib.scs_finish.argtypes = [C.c_void_p]
+lib.scs_set_default_settings.restype = None
+lib.scs_set_default_settings.argtypes = [C.POINTER(ScsSettings)]
+lib.scs_version.restype = C.c_char_p
+lib.scs_get_lin_sys_method.restype = C.c_char_p
+lib.scs_init_lin_sys_work.restype = C.c_void_p
+lib.scs_init_lin_sys_work.argtypes = [C.POINTER(ScsMatrix), C.POINTER(ScsMatrix), p_double]
+lib.scs_free_lin_sys_work.restype = None
+lib.scs_free_lin_sys_work.argtypes = [C.c_void_p]
+lib.scs_solve_lin_sys.restype = c_int
+lib.scs_solve_lin_sys.argtypes = [C.c_void_p, p_double, p_double, c_double]
+lib.scs_update_lin_sys_diag_r.restype = c_int
+lib.scs_update_lin_sys_diag_r.argtypes = [C.c_void_p, p_double]
+lib.scs_b200_lin_sys_cg_its.restype = c_int
+lib.scs_b200_lin_sys_cg_its.argtypes = [C.c_void_p]
+lib.scs_b200_init_cone.restype = C.c_void_p
+lib.scs_b200_init_cone.argtypes = [C.POINTER(ScsCone), c_int]
+lib.scs_b200_proj_dual_cone.restype = c_int
+lib.scs_b200_proj_dual_cone.argtypes = [p_double, C.c_void_p, p_double, p_double]
+lib.scs_b200_finish_cone.restype = None
+lib.scs_b200_finish_cone.argtypes = [C.c_void_p]
+for _f in ("scs_b200_accum_by_a", "scs_b200_accum_by_atrans", "scs_b200_accum_by_p"):
+    getattr(lib, _f).restype = c_int
+    getattr(lib, _f).argtypes = [C.POINTER(ScsMatrix), p_double, p_double]
+lib.scs_b200_aa_init.restype = C.c_void_p
+lib.scs_b200_aa_init.argtypes = [c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_int]
+lib.scs_b200_aa_apply.restype = c_double
+lib.scs_b200_aa_apply.argtypes = [p_double, p_double, C.c_void_p]
+lib.scs_b200_aa_safeguard.restype = c_int
+lib.scs_b200_aa_safeguard.argtypes = [p_double, p_double, C.c_void_p]
+lib.scs_b200_aa_reset.restype = None
+lib.scs_b200_aa_reset.argtypes = [C.c_void_p]
+lib.scs_b200_aa_get_stats.restype = AaStats
+lib.scs_b200_aa_get_stats.argtypes = [C.c_void_p]
+lib.scs_b200_aa_finish.restype = None
+lib.scs_b200_aa_finish.argtypes = [C.c_void_p]
+lib.scs_b200_set_device.restype = c_int
+lib.scs_b200_set_device.argtypes = [c_int]
+lib.scs_b200_device_count.restype = c_int
+lib.scs_b200_get_stats.restype = c_int
+lib.scs_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(ScsB200Stats)]
+lib.scs_b200_bench_spmv.restype = c_double
+lib.scs_b200_bench_spmv.argtypes = [C.c_void_p, c_int, c_int, p_double]
+
+
+def version():
+    return lib.scs_version().decode()
+
+
+def sizeof_int():
+    return C.sizeof(c_int)
+
+
+def sizeof_float():
+    return C.sizeof(c_double)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(p_double)
+
+
+def _iptr(a):
+    return a.ctypes.data_as(p_int)
+
+
+def make_matrix(x, i, p, m, n):
+    """ScsMatrix view over contiguous numpy arrays (kept alive by the caller)."""
+    return ScsMatrix(_dptr(x), _iptr(i), _iptr(p), int(m), int(n))
+
+
+def _check_float_1d(a, name):
+    if not isinstance(a, np.ndarray) or a.dtype.kind != "f" or a.ndim != 1:
+        raise TypeError("%s must be a 1-D numpy array of floats" % name)
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _check_int_1d(a, name):
+    if not isinstance(a, np.ndarray) or a.dtype.kind not in "iu" or a.ndim != 1:
+        raise TypeError("%s must be a 1-D numpy array of ints" % name)
+    if a.size and (a.max() > np.iinfo(np.int32).max):
+        raise ValueError("%s exceeds the 32-bit index range of the B200 backend" % name)
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _pos_int(cone, key):
+    if key not in cone or cone[key] is None:
+        return 0
+    v = cone[key]
+    if isinstance(v, bool) or not isinstance(v, (int, np.integer)) or v < 0 or v > np.iinfo(np.int32).max:
+        raise ValueError("Invalid value for cone field '%s'" % key)
+    return int(v)
+
+
+def _int_arr(cone, key):
+    if key not in cone or cone[key] is None:
+        return np.zeros(0, dtype=np.int32)
+    v = cone[key]
+    if isinstance(v, (int, np.integer)) and not isinstance(v, bool):
+        v = [v]
+    if isinstance(v, np.ndarray):
+        if v.dtype.kind not in "iu" or v.ndim != 1:
+            raise ValueError("Invalid value for cone field '%s'" % key)
+        v = v.tolist()
+    if not isinstance(v, (list, tuple)):
+        raise ValueError("Invalid value for cone field '%s'" % key)
+    for e in v:
+        if isinstance(e, bool) or not isinstance(e, (int, np.integer)) or e < 0:
+            raise ValueError("Invalid value for cone field '%s'" % key)
+    return np.asarray(v, dtype=np.int32).reshape(-1)
+
+
+def _float_arr(cone, key):
+    if key not in cone or cone[key] is None:
+        return np.zeros(0, dtype=np.float64)
+    v = cone[key]
+    if isinstance(v, (int, float, np.integer, np.floating)) and not isinstance(v, bool):
+        v = [v]
+    if isinstance(v, np.ndarray):
+        if v.dtype.kind != "f" or v.ndim != 1:
+            raise ValueError("Invalid value for cone field '%s'" % key)
+    try:
+        return np.asarray(v, dtype=np.float64).reshape(-1)
+    except (TypeError, ValueError):
+        raise ValueError("Invalid value for cone field '%s'" % key)
+
+
+def make_cone(cone):
+    """Python cone dict -> (ScsCone, keepalive) with the parsing rules of scsobject.h:684-794."""
+    keep = {}
+    k = ScsCone()
+    f = _pos_int(cone, "f")
+    k.z = _pos_int(cone, "z")
+    if f > 0:
+        warnings.warn("The 'f' cone field is deprecated; use 'z' (Zero cone) instead. "
+                      "If both 'f' and 'z' are set they are summed.", DeprecationWarning, stacklevel=3)
+        k.z += f
+    k.l = _pos_int(cone, "l")
+    bu, bl = _float_arr(cone, "bu"), _float_arr(cone, "bl")
+    if len(bu) != len(bl):
+        raise ValueError("bu different dimension to bl")
+    keep["bu"], keep["bl"] = bu, bl
+    if len(bu) > 0:
+        k.bsize = len(bu) + 1
+        k.bu, k.bl = _dptr(bu), _dptr(bl)
+    for key, fld, sz in (("q", "q", "qsize"), ("s", "s", "ssize"), ("cs", "cs", "cssize")):
+        arr = _int_arr(cone, key)
+        keep[key] = arr
+        setattr(k, sz, len(arr))
+        if len(arr):
+            setattr(k, fld, _iptr(arr))
+    p = _float_arr(cone, "p")
+    keep["p"] = p
+    k.psize = len(p)
+    if len(p):
+        k.p = _dptr(p)
+    k.ep = _pos_int(cone, "ep")
+    k.ed = _pos_int(cone, "ed")
+    return k, keep
+
+
+_SETTING_KEYS = ("verbose", "normalize", "adaptive_scale", "max_iters", "scale", "eps_abs", "eps_rel",
+                 "eps_infeas", "alpha", "rho_x", "time_limit_secs", "acceleration_lookback",
+                 "acceleration_interval", "acceleration_type_1", "acceleration_regularization",
+                 "acceleration_relaxation", "write_data_filename", "log_csv_filename")
+_BOOL_KEYS = ("verbose", "normalize", "adaptive_scale")
+_INT_KEYS = ("max_iters", "acceleration_lookback", "acceleration_interval", "acceleration_type_1")
+
+
+def make_settings(kwargs):
+    """kwargs -> ScsSettings with the type and range checks of scsobject.h:500-868."""
+    st = ScsSettings()
+    lib.scs_set_default_settings(C.byref(st))
+    keep = []
+    for key, val in kwargs.items():
+        if key not in _SETTING_KEYS:
+            raise TypeError("'%s' is an invalid keyword argument for SCS()" % key)
+        if key in _BOOL_KEYS:
+            if not isinstance(val, (bool, np.bool_)):
+                raise TypeError("argument '%s' must be bool, not %s" % (key, type(val).__name__))
+            setattr(st, key, 1 if val else 0)
+        elif key in _INT_KEYS:
+            if isinstance(val, (bool, np.bool_)):
+                val = int(val)
+            if not isinstance(val, (int, np.integer)):
+                raise TypeError("argument '%s' must be int, not %s" % (key, type(val).__name__))
+            if abs(int(val)) > np.iinfo(np.int32).max:
+                raise OverflowError("signed integer is greater than maximum")
+            setattr(st, key, int(val))
+        elif key in ("write_data_filename", "log_csv_filename"):
+            if val is not None:
+                if not isinstance(val, str):
+                    raise TypeError("argument '%s' must be str or None" % key)
+                b = val.encode()
+                keep.append(b)
+                setattr(st, key, b)
+        else:
+            if isinstance(val, (bool, np.bool_)) or not isinstance(val, (int, float, np.integer, np.floating)):
+                raise TypeError("argument '%s' must be float, not %s" % (key, type(val).__name__))
+            setattr(st, key, float(val))
+    if st.max_iters <= 0:
+        raise ValueError("max_iters must be positive")
+    if st.acceleration_lookback < 0:
+        raise ValueError("acceleration_lookback must be nonnegative (use acceleration_type_1=0 for type-II AA)")
+    if st.acceleration_interval <= 0:
+        raise ValueError("acceleration_interval must be positive")
+    if not math.isfinite(st.acceleration_regularization) or st.acceleration_regularization < 0:
+        raise ValueError("acceleration_regularization must be a nonnegative finite number")
+    if (not math.isfinite(st.acceleration_relaxation) or st.acceleration_relaxation < 0
+            or st.acceleration_relaxation > 2):
+        raise ValueError("acceleration_relaxation must be in [0, 2]")
+    if not math.isfinite(st.scale) or st.scale <= 0:
+        raise ValueError("scale must be a positive finite number")
+    if math.isnan(st.time_limit_secs) or st.time_limit_secs < 0:
+        raise ValueError("time_limit_secs must be nonnegative")
+    for key in ("eps_abs", "eps_rel", "eps_infeas"):
+        v = getattr(st, key)
+        if math.isnan(v) or v < 0:
+            raise ValueError("%s must be nonnegative" % key)
+    if not math.isfinite(st.alpha) or st.alpha <= 0 or st.alpha >= 2:
+        raise ValueError("alpha must be in (0, 2)")
+    if not math.isfinite(st.rho_x) or st.rho_x <= 0:
+        raise ValueError("rho_x must be a positive finite number")
+    st.warm_start = 0
+    return st, keep
+
+
+_INFO_KEYS = ("status_val", "iter", "scale_updates", "scale", "pobj", "dobj", "res_pri", "res_dual", "gap",
+              "res_infeas", "res_unbdd_a", "res_unbdd_p", "comp_slack", "solve_time", "setup_time",
+              "lin_sys_time", "cone_time", "accel_time", "rejected_accel_steps", "accepted_accel_steps")
+_AA_KEYS = ("iter", "n_accept", "n_reject_lapack", "n_reject_rank0", "n_reject_nonfinite",
+            "n_reject_weight_cap", "n_safeguard_reject", "last_rank", "last_aa_norm", "last_regularization")
+
+
+class SCS(object):
+    """Same constructor / methods as the extension type `scs.SCS` (scsobject.h:1261-1307)."""
+
+    def __init__(self, shape, Ax, Ai, Ap, Px, Pi, Pp, b, c, cone, **settings):
+        self._work = None
+        self._lock = threading.Lock()
+        m, n = int(shape[0]), int(shape[1])
+        if m <= 0:
+            raise ValueError("m must be a positive integer")
+        if n <= 0:
+            raise ValueError("n must be a positive integer")
+        if not isinstance(cone, dict):
+            raise TypeError("cone must be a dict")
+        self.m, self.n = m, n
+        Ax = _check_float_1d(Ax, "Ax")
+        Ai = _check_int_1d(Ai, "Ai")
+        Ap = _check_int_1d(Ap, "Ap")
+        A = make_matrix(Ax, Ai, Ap, m, n)
+        P = None
+        if Px is not None and Pi is not None and Pp is not None:
+            Px = _check_float_1d(Px, "Px")
+            Pi = _check_int_1d(Pi, "Pi")
+            Pp = _check_int_1d(Pp, "Pp")
+            P = make_matrix(Px, Pi, Pp, n, n)
+        c = _check_float_1d(c, "c")
+        if c.shape[0] != n:
+            raise ValueError("c has incompatible dimension with A")
+        b = _check_float_1d(b, "b")
+        if b.shape[0] != m:
+            raise ValueError("b has incompatible dimension with A")
+        if len(Ap) != n + 1:
+            raise ValueError("Ap has incompatible dimension with A")
+        k, keep_cone = make_cone(cone)
+        stgs, keep_stgs = make_settings(settings)
+        d = ScsData(m, n, C.pointer(A), C.pointer(P) if P is not None else None, _dptr(b), _dptr(c))
+        self._x = np.zeros(n)
+        self._y = np.zeros(m)
+        self._s = np.zeros(m)
+        self._sol = ScsSolution(_dptr(self._x), _dptr(self._y), _dptr(self._s))
+        work = lib.scs_init(C.byref(d), C.byref(k), C.byref(stgs))  # ctypes releases the GIL
+        del keep_cone, keep_stgs
+        if not work:
+            raise ValueError("ScsWork allocation error!")
+        self._work = C.c_void_p(work)
+
+    def solve(self, warm_start, x, y, s):
+        if not isinstance(warm_start, (bool, np.bool_)):
+            raise TypeError("argument 1 must be bool, not %s" % type(warm_start).__name__)
+        with self._lock:
+            if not self._work:
+                raise ValueError("Workspace not initialized!")
+            if warm_start:
+                for name, dst, src, ln in (("x", self._x, x, self.n), ("y", self._y, y, self.m),
+                                           ("s", self._s, s, self.m)):
+                    if src is None:
+                        continue
+                    if (not isinstance(src, np.ndarray) or src.dtype.kind != "f" or src.ndim != 1
+                            or src.shape[0] != ln):
+                        raise ValueError("Warm-start must be a 1-D float array of length %d" % ln)
+                    dst[:] = src
+            info = ScsInfo()
+            lib.scs_solve(self._work, C.byref(self._sol), C.byref(info), 1 if warm_start else 0)
+            out_x, out_y, out_s = self._x.copy(), self._y.copy(), self._s.copy()
+        info_dict = {key: getattr(info, key) for key in _INFO_KEYS}
+        info_dict["status"] = info.status.decode()
+        info_dict["lin_sys_solver"] = info.lin_sys_solver.decode()
+        info_dict["aa_stats"] = {key: getattr(info.aa_stats, key) for key in _AA_KEYS}
+        return {"x": out_x, "y": out_y, "s": out_s, "info": info_dict}
+
+    def update(self, b, c):
+        bb = cc = None
+        if c is not None:
+            if not isinstance(c, np.ndarray) or c.dtype.kind != "f" or c.ndim != 1:
+                raise TypeError("c_new must be a 1-D numpy array of floats")
+            if c.shape[0] != self.n:
+                raise ValueError("c_new has incompatible dimension with A")
+            cc = np.ascontiguousarray(c, dtype=np.float64)
+        if b is not None:
+            if not isinstance(b, np.ndarray) or b.dtype.kind != "f" or b.ndim != 1:
+                raise TypeError("b_new must be a 1-D numpy array of floats")
+            if b.shape[0] != self.m:
+                raise ValueError("b_new has incompatible dimension with A")
+            bb = np.ascontiguousarray(b, dtype=np.float64)
+        with self._lock:
+            if not self._work:
+                raise ValueError("Workspace not initialized!")
+            lib.scs_update(self._work, _dptr(bb) if bb is not None else None, _dptr(cc) if cc is not None else None)
+
+    # --- B200-only extras (no reference counterpart) ---
+    def stats(self):
+        st = ScsB200Stats()
+        with self._lock:
+            if not self._work:
+                raise ValueError("Workspace not initialized!")
+            lib.scs_b200_get_stats(self._work, C.byref(st))
+        return {f: getattr(st, f) for f, _ in ScsB200Stats._fields_}
+
+    def bench_spmv(self, which, reps):
+        ab = c_double(0.0)
+        with self._lock:
+            ms = lib.scs_b200_bench_spmv(self._work, int(which), int(reps), C.byref(ab))
+        return ms, ab.value
+
+    def finish(self):
+        with self._lock:
+            if self._work:
+                lib.scs_finish(self._work)
+                self._work = None
+
+    def __del__(self):
+        try:
+            self.finish()
+        except Exception:
+            pass

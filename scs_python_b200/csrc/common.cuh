@@ -1,0 +1,259 @@
+// common.cuh -- shared device/host infrastructure of libscsb200 (sm_100a only).
+//
+//  * Ctx        : per-workspace CUDA context (device, stream, reduction scratch, counters)
+//  * grid_reduce: deterministic grid-wide multi-value sum/max with "last block finishes"
+//                 finalisation, so data-dependent scalars (CG alpha/beta, tau, tolerances)
+//                 are produced and consumed on the device and never cross to the host.
+//  * DevScalars : the block of device-resident scalars of one workspace.
+#pragma once
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/scs_b200.h"
+
+namespace b200 {
+
+constexpr int kThreads = 256;    // CTA size of every streaming kernel
+constexpr int kMaxRedVals = 24;  // max simultaneous reduction outputs of one kernel
+constexpr int kCtasPerSm = 8;    // resident 256-thread CTAs per SM (2048 threads / SM)
+
+#define B200_PRINTF(...)          \
+  do {                            \
+    fprintf(stdout, __VA_ARGS__); \
+    fflush(stdout);               \
+  } while (0)
+
+#define CUDA_OK(call)                                                                     \
+  do {                                                                                    \
+    cudaError_t err__ = (call);                                                           \
+    if (err__ != cudaSuccess) {                                                           \
+      fprintf(stderr, "libscsb200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(err__), \
+              __FILE__, __LINE__, cudaGetErrorString(err__));                             \
+      return -1;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+#define CUDA_OK_NULL(call)                                                                \
+  do {                                                                                    \
+    cudaError_t err__ = (call);                                                           \
+    if (err__ != cudaSuccess) {                                                           \
+      fprintf(stderr, "libscsb200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(err__), \
+              __FILE__, __LINE__, cudaGetErrorString(err__));                             \
+      return nullptr;                                                                     \
+    }                                                                                     \
+  } while (0)
+
+// Workspace of grid_reduce: partials[k * stride + block], ticket counter.
+struct RedWs {
+  double *partials;
+  unsigned int *ticket;
+  int stride;
+};
+
+// Device-resident scalars of one workspace.  Written by the finalising block of the
+// producing kernel, read by every thread of the consuming kernels.
+struct DevScalars {
+  // --- ADMM ---
+  double vnorm2;       // sum_j v_j^2 of the current v (for normalize_v, scs.c:771-779)
+  double tau;          // u_t[l-1] from root_plus (scs.c:667-688)
+  double nm_ax_s_btau; // ||Ax+s-b tau||_inf, normalised, from the last residual check
+  double nm_px_aty_ctau;
+  // --- PCG (cpu/indirect/private.c:135-219) ---
+  double cg_tol;
+  double ztr, pGp, alpha, beta, norm_r;
+  int cg_done;   // 1: converged / nothing to do; CG kernels exit immediately
+  int zero_rhs;  // 1: ||rhs||_inf <= 1e-12 -> solution is 0 (private.c:288-291)
+  int cg_its;    // CG iterations of the current solve
+  int cg_its_total;
+  // --- AA (aa.c) ---
+  double aa_norm;  // return value of aa_apply for the current ADMM iteration
+  int aa_rejected, aa_accepted;  // safeguard counters of the current solve
+  int pad0;
+  // --- residual block, filled every CONVERGED_INTERVAL iterations (scs.c:513-585) ---
+  double res[32];
+  // --- misc results of setup / finalisation reductions ---
+  double sigma;      // primal_scale == dual_scale (normalize.c:46-60)
+  double fin[4];     // ||s||_inf, ||y||_inf, s'y of the un-normalised solution (scs.c:885-887)
+};
+
+// indices into DevScalars::res
+enum ResIdx {
+  R_TAU = 0, R_KAP,
+  R_BTY_TAU, R_CTX_TAU, R_XPX_TAU,
+  R_NM_AX_S_BTAU, R_NM_AX_S, R_NM_AX,          // normalised inf-norms (m-space)
+  R_NM_PX_ATY_CTAU, R_NM_PX, R_NM_ATY,         // normalised inf-norms (n-space)
+  R_ONM_AX_S_BTAU, R_ONM_AX_S, R_ONM_AX, R_ONM_S,  // un-normalised (divided by D*dual_scale)
+  R_ONM_PX_ATY_CTAU, R_ONM_PX, R_ONM_ATY,      // un-normalised (divided by E*primal_scale)
+  R_COUNT
+};
+
+struct Ctx {
+  int device = 0;
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  RedWs red{nullptr, nullptr, 0};
+  DevScalars *S = nullptr;       // device
+  DevScalars *S_host = nullptr;  // pinned mirror
+  cudaEvent_t ev = nullptr;
+  // counters
+  long long launches = 0, spmv_calls = 0, h2d = 0, d2h = 0;
+  int grid_ew() const { return sms * kCtasPerSm; }
+
+  int init(int dev) {
+    device = dev;
+    CUDA_OK(cudaSetDevice(device));
+    int v = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    sms = v > 0 ? v : 148;
+    CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    own_stream = true;
+    red.stride = grid_ew();
+    CUDA_OK(cudaMalloc(&red.partials, sizeof(double) * kMaxRedVals * red.stride));
+    CUDA_OK(cudaMalloc(&red.ticket, sizeof(unsigned int)));
+    CUDA_OK(cudaMemsetAsync(red.ticket, 0, sizeof(unsigned int), stream));
+    CUDA_OK(cudaMalloc(&S, sizeof(DevScalars)));
+    CUDA_OK(cudaMemsetAsync(S, 0, sizeof(DevScalars), stream));
+    CUDA_OK(cudaMallocHost(&S_host, sizeof(DevScalars)));
+    memset(S_host, 0, sizeof(DevScalars));
+    CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    return 0;
+  }
+  void destroy() {
+    cudaSetDevice(device);
+    if (red.partials) cudaFree(red.partials);
+    if (red.ticket) cudaFree(red.ticket);
+    if (S) cudaFree(S);
+    if (S_host) cudaFreeHost(S_host);
+    if (ev) cudaEventDestroy(ev);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+    red = RedWs{nullptr, nullptr, 0};
+    S = nullptr; S_host = nullptr; ev = nullptr; stream = nullptr;
+  }
+  // copy the device scalar block to the pinned mirror and wait for it
+  int fetch_scalars() {
+    CUDA_OK(cudaMemcpyAsync(S_host, S, sizeof(DevScalars), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    d2h += sizeof(DevScalars);
+    return 0;
+  }
+  int sync() {
+    CUDA_OK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+};
+
+template <class T>
+inline int dev_alloc(T **p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  CUDA_OK(cudaMalloc((void **)p, count * sizeof(T)));
+  return 0;
+}
+template <class T>
+inline int dev_alloc_zero(T **p, size_t count, cudaStream_t st) {
+  if (dev_alloc(p, count)) return -1;
+  CUDA_OK(cudaMemsetAsync(*p, 0, (count ? count : 1) * sizeof(T), st));
+  return 0;
+}
+template <class T>
+inline void dev_free(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+template <class T>
+inline int h2d(Ctx &c, T *dst, const T *src, size_t count) {
+  if (!count) return 0;
+  CUDA_OK(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, c.stream));
+  c.h2d += (long long)(count * sizeof(T));
+  return 0;
+}
+template <class T>
+inline int d2h(Ctx &c, T *dst, const T *src, size_t count) {
+  if (!count) return 0;
+  CUDA_OK(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, c.stream));
+  c.d2h += (long long)(count * sizeof(T));
+  return 0;
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ device helpers ----
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// NaN-propagating |.|-max used for inf-norms: fmax() drops NaNs, the reference's loop
+// (linalg.c norm_inf) keeps the running max, so NaN is ignored there as well.
+__device__ __forceinline__ double absmax(double a, double x) { return fmax(a, fabs(x)); }
+
+// Block-wide reduction of NS sums followed by NM maxes held in vals[0..NS+NM).
+// Result valid in thread 0.  sh must hold (NS+NM)*32 doubles.
+template <int NS, int NM>
+__device__ __forceinline__ void block_reduce(double *vals, double *sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NS + NM; ++k) vals[k] = (k < NS) ? warp_sum(vals[k]) : warp_max(vals[k]);
+  __syncthreads();  // protect sh from a previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NS + NM; ++k) sh[k * 32 + wid] = vals[k];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < NS + NM; ++k) {
+      double v = (lane < nw) ? sh[k * 32 + lane] : ((k < NS) ? 0.0 : -INFINITY);
+      vals[k] = (k < NS) ? warp_sum(v) : warp_max(v);
+    }
+  }
+}
+
+// Deterministic grid-wide reduction.  Every thread of every block must call it exactly
+// once per kernel.  vals[0..NS) are summed, vals[NS..NS+NM) are maxed.  The last block to
+// arrive re-reduces the per-block partials in a fixed order and calls fin(vals) on its
+// thread 0, then re-arms the ticket.  Requires gridDim.x <= ws.stride.
+template <int NS, int NM, class Fin>
+__device__ __forceinline__ void grid_reduce(double *vals, const RedWs &ws, Fin fin) {
+  __shared__ double sh[(NS + NM) * 32];
+  __shared__ int is_last;
+  block_reduce<NS, NM>(vals, sh);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NS + NM; ++k) ws.partials[k * ws.stride + blockIdx.x] = vals[k];
+    __threadfence();
+    unsigned int t = atomicAdd(ws.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < NS + NM; ++k) {
+    double v = (k < NS) ? 0.0 : -INFINITY;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      double pv = __ldcg(&ws.partials[k * ws.stride + b]);
+      v = (k < NS) ? (v + pv) : fmax(v, pv);
+    }
+    vals[k] = v;
+  }
+  block_reduce<NS, NM>(vals, sh);
+  if (threadIdx.x == 0) {
+    fin(vals);
+    *ws.ticket = 0u;
+    __threadfence();
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace b200

@@ -1,0 +1,477 @@
+// linsys.cu -- PCG kernels, the LinSys driver and the ScsLinSysWork plugin ABI.
+#include "linsys.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------- epilogues ---
+// b[j] += (A' tmp)_j                                     (private.c:297)
+struct EpiRhs : EpiNoState {
+  double *b;
+  __device__ __forceinline__ void row(State &, int j, double acc) const { b[j] += acc; }
+};
+// out[i] = (A x)_i / R_y,i                               (private.c:116-117)
+struct EpiScaleRy : EpiNoState {
+  double *out;
+  const double *ry;  // diag_r + n
+  __device__ __forceinline__ void row(State &, int i, double acc) const { out[i] = acc / ry[i]; }
+};
+// Gp_j = (A' z)_j + (P p)_j + R_x,j p_j ; p'Gp ; alpha = z'r / p'Gp     (private.c:181-183)
+struct EpiG {
+  static constexpr bool kSeparate = false;
+  struct State { double pgp; };
+  __device__ __forceinline__ void row2(State &, int, double, double) const {}
+  double *Gp;
+  const double *p, *rx;
+  __device__ __forceinline__ void init(State &s) const { s.pgp = 0.0; }
+  __device__ __forceinline__ void row(State &s, int j, double acc) const {
+    const double pj = p[j];
+    const double g = acc + rx[j] * pj;
+    Gp[j] = g;
+    s.pgp = fma(pj, g, s.pgp);
+  }
+  __device__ __forceinline__ void finish(State &s, const RedWs &ws, DevScalars *S) const {
+    double v[1] = {s.pgp};
+    grid_reduce<1, 0>(v, ws, [S](double *o) {
+      S->pGp = o[0];
+      S->alpha = S->ztr / o[0];
+    });
+  }
+};
+// warm-started start of CG: r = b - G s ; x = s ; z = M r ; p = z ; z'r ; ||r||_inf
+//                                                       (private.c:153-174)
+struct EpiG0 {
+  static constexpr bool kSeparate = false;
+  struct State { double ztr, nr; };
+  __device__ __forceinline__ void row2(State &, int, double, double) const {}
+  double *b;  // in: rhs, out: x = s
+  const double *s, *rx, *M;
+  double *r, *z, *p;
+  __device__ __forceinline__ void init(State &st) const { st.ztr = 0.0; st.nr = 0.0; }
+  __device__ __forceinline__ void row(State &st, int j, double acc) const {
+    const double sj = s[j];
+    const double rj = b[j] - (acc + rx[j] * sj);
+    const double zj = rj * M[j];
+    b[j] = sj;
+    r[j] = rj;
+    z[j] = zj;
+    p[j] = zj;
+    st.ztr = fma(zj, rj, st.ztr);
+    st.nr = fmax(st.nr, fabs(rj));
+  }
+  __device__ __forceinline__ void finish(State &st, const RedWs &ws, DevScalars *S) const {
+    double v[2] = {st.ztr, st.nr};
+    grid_reduce<1, 1>(v, ws, [S](double *o) {
+      S->ztr = o[0];
+      S->norm_r = o[1];
+      S->cg_done = (o[1] < fmax(S->cg_tol, 1e-12)) ? 1 : 0;
+    });
+  }
+};
+// y_i = ((A x)_i - ry_i) / R_y,i   written over ry      (private.c:304-309)
+struct EpiY : EpiNoState {
+  double *by;        // b + n
+  const double *ry;  // diag_r + n
+  __device__ __forceinline__ void row(State &, int i, double acc) const { by[i] = (acc - by[i]) / ry[i]; }
+};
+// M_j = 1 / (R_x,j + sum_k A_kj^2 / R_y,k + P_jj)        (private.c:60-80)
+struct EpiPrecond : EpiNoState {
+  double *M;
+  const double *rx, *Pdiag;
+  __device__ __forceinline__ void row(State &, int j, double acc) const { M[j] = 1.0 / ((rx[j] + acc) + Pdiag[j]); }
+};
+
+// --------------------------------------------------------------------------- kernels ---
+// tmp = ry ./ R_y                                         (private.c:293-295)
+__global__ void __launch_bounds__(kThreads)
+k_scale_ry(const double *__restrict__ by, const double *__restrict__ ry, double *__restrict__ tmp, int m,
+           const int *skip) {
+  if (*skip) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) tmp[i] = by[i] / ry[i];
+}
+
+// cold start of CG (s == NULL): r = b ; x = 0 ; z = M r ; p = z      (private.c:147-152,170-174)
+__global__ void __launch_bounds__(kThreads)
+k_cg_init_cold(double *__restrict__ b, const double *__restrict__ M, double *__restrict__ r,
+               double *__restrict__ z, double *__restrict__ p, int n, RedWs ws, DevScalars *S) {
+  if (S->cg_done) return;
+  double v[2] = {0.0, 0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const double rj = b[j];
+    const double zj = rj * M[j];
+    b[j] = 0.0;
+    r[j] = rj;
+    z[j] = zj;
+    p[j] = zj;
+    v[0] = fma(zj, rj, v[0]);
+    v[1] = fmax(v[1], fabs(rj));
+  }
+  grid_reduce<1, 1>(v, ws, [S](double *o) {
+    S->ztr = o[0];
+    S->norm_r = o[1];
+    S->cg_done = (o[1] < fmax(S->cg_tol, 1e-12)) ? 1 : 0;
+  });
+}
+
+// x += alpha p ; r -= alpha Gp ; z = M r ; z'r ; ||r||_inf ; stop test ; beta
+//                                                       (private.c:184-213)
+__global__ void __launch_bounds__(kThreads)
+k_cg_update(double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, const double *__restrict__ p,
+            const double *__restrict__ Gp, const double *__restrict__ M, int n, RedWs ws, DevScalars *S) {
+  if (S->cg_done) return;
+  const double alpha = S->alpha;
+  double v[2] = {0.0, 0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    x[j] = fma(alpha, p[j], x[j]);
+    const double rj = fma(-alpha, Gp[j], r[j]);
+    const double zj = rj * M[j];
+    r[j] = rj;
+    z[j] = zj;
+    v[0] = fma(zj, rj, v[0]);
+    v[1] = fmax(v[1], fabs(rj));
+  }
+  grid_reduce<1, 1>(v, ws, [S](double *o) {
+    const double ztr_prev = S->ztr;
+    S->cg_its += 1;
+    S->cg_its_total += 1;
+    S->norm_r = o[1];
+    S->ztr = o[0];
+    S->beta = o[0] / ztr_prev;
+    if (o[1] < S->cg_tol || ztr_prev == 0.0 || !(o[1] == o[1])) S->cg_done = 1;
+  });
+}
+
+// p = z + beta p                                         (private.c:213-216)
+__global__ void __launch_bounds__(kThreads)
+k_cg_pupdate(double *__restrict__ p, const double *__restrict__ z, int n, const DevScalars *S) {
+  if (S->cg_done) return;
+  const double beta = S->beta;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    p[j] = fma(beta, p[j], z[j]);
+}
+
+// b = 0 when the right-hand side was (numerically) zero   (private.c:288-291)
+__global__ void __launch_bounds__(kThreads) k_zero_if(double *__restrict__ b, int len, const int *flag) {
+  if (!*flag) return;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) b[j] = 0.0;
+}
+
+// S->cg_tol = tol ; zero_rhs = (||b||_inf <= 1e-12) ; cg_done = zero_rhs ; cg_its = 0
+__global__ void __launch_bounds__(kThreads)
+k_prepare_flags(const double *__restrict__ b, int len, double tol, RedWs ws, DevScalars *S) {
+  double v[1] = {0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x)
+    v[0] = fmax(v[0], fabs(b[j]));
+  grid_reduce<0, 1>(v, ws, [S, tol](double *o) {
+    S->cg_tol = tol;
+    S->zero_rhs = (o[0] <= 1e-12) ? 1 : 0;
+    S->cg_done = S->zero_rhs;
+    S->cg_its = 0;
+  });
+}
+
+// ---------------------------------------------------------------------------- driver ---
+static inline int ew_grid(const Ctx &c, long long len) {
+  long long g = (len + kThreads - 1) / kThreads;
+  if (g < 1) g = 1;
+  return (int)(g < c.grid_ew() ? g : c.grid_ew());
+}
+
+int LinSys::init(Ctx *ctx, const ScsMatrix *Ah, const ScsMatrix *Ph) {
+  c = ctx;
+  n = Ah->n;
+  m = Ah->m;
+  CUDA_OK(cudaSetDevice(c->device));
+  if (csr_upload(*c, At, n, m, Ah->p, Ah->i, Ah->x)) return -1;  // CSC(A) == CSR(A')
+  if (csr_transpose(*c, At, A)) return -1;                       // CSR(A) on the device
+  hasP = (Ph != nullptr);
+  std::vector<double> pd((size_t)n, 0.0);
+  if (hasP) {
+    if (csr_from_upper_csc(*c, P, n, Ph->p, Ph->i, Ph->x)) return -1;
+    for (int j = 0; j < n; ++j) {  // diagonal is the last entry of an upper-tri sorted column
+      const int last = Ph->p[j + 1] - 1;
+      if (last >= Ph->p[j] && Ph->i[last] == j) pd[j] = Ph->x[last];
+    }
+  } else {
+    P = CsrDev();
+    P.nrows = P.ncols = n;
+    if (dev_alloc_zero(&P.ptr, (size_t)n + 1, c->stream)) return -1;  // empty rows
+  }
+  if (dev_alloc(&Pdiag, (size_t)n) || h2d(*c, Pdiag, pd.data(), (size_t)n)) return -1;
+  if (c->sync()) return -1;
+  if (chunks_build(*c, chA, A, nullptr)) return -1;
+  if (chunks_build(*c, chAt, At, hasP ? &P : nullptr)) return -1;
+  if (dev_alloc_zero(&M, (size_t)n, c->stream) || dev_alloc_zero(&p, (size_t)n, c->stream) ||
+      dev_alloc_zero(&r, (size_t)n, c->stream) || dev_alloc_zero(&Gp, (size_t)n, c->stream) ||
+      dev_alloc_zero(&z, (size_t)n, c->stream) || dev_alloc_zero(&tmp, (size_t)m, c->stream))
+    return -1;
+  return 0;
+}
+
+int LinSys::finalize_structure() { return 0; }
+
+void LinSys::destroy() {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  csr_free(A);
+  csr_free(At);
+  csr_free(P);
+  chunks_free(chA);
+  chunks_free(chAt);
+  if (own_diag_r) dev_free(diag_r);
+  diag_r = nullptr;
+  dev_free(Pdiag);
+  dev_free(M); dev_free(p); dev_free(r); dev_free(Gp); dev_free(z); dev_free(tmp);
+}
+
+// Refresh P's diagonal from the (possibly re-scaled) device copy of P.
+__global__ void __launch_bounds__(kThreads) k_extract_diag(CsrDev P, double *__restrict__ d) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P.nrows; j += gridDim.x * blockDim.x) {
+    double v = 0.0;
+    for (int k = P.ptr[j]; k < P.ptr[j + 1]; ++k)
+      if (P.idx[k] == j) v = P.val[k];
+    d[j] = v;
+  }
+}
+
+int LinSys::update_precond() {
+  if (hasP) {
+    k_extract_diag<<<ew_grid(*c, n), kThreads, 0, c->stream>>>(P, Pdiag);
+    c->launches++;
+  }
+  EpiPrecond epi;
+  epi.M = M; epi.rx = diag_r; epi.Pdiag = Pdiag;
+  ElemSqDiv e{diag_r + n};
+  row_kernel<ElemSqDiv, ElemSqDiv, EpiPrecond, false>
+      <<<chAt.grid, kThreads, 0, c->stream>>>(At, e, At, e, chAt.d, chAt.n, epi, c->red, c->S, nullptr);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int LinSys::launch_A_scaled(const double *x, double *out, const int *skip) {
+  EpiScaleRy epi;
+  epi.out = out; epi.ry = diag_r + n;
+  ElemMul e{x};
+  row_kernel<ElemMul, ElemMul, EpiScaleRy, false>
+      <<<chA.grid, kThreads, 0, c->stream>>>(A, e, A, e, chA.d, chA.n, epi, c->red, c->S, skip);
+  c->launches++; c->spmv_calls++;
+  return 0;
+}
+
+int LinSys::launch_G(const double *zin, const double *pin, double *out, const int *skip) {
+  EpiG epi;
+  epi.Gp = out; epi.p = pin; epi.rx = diag_r;
+  ElemMul ea{zin}, eb{pin};
+  if (hasP)
+    row_kernel<ElemMul, ElemMul, EpiG, true>
+        <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, P, eb, chAt.d, chAt.n, epi, c->red, c->S, skip);
+  else
+    row_kernel<ElemMul, ElemMul, EpiG, false>
+        <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, P, eb, chAt.d, chAt.n, epi, c->red, c->S, skip);
+  c->launches++; c->spmv_calls++;
+  return 0;
+}
+
+int LinSys::prepare_flags(const double *b, double tol) {
+  k_prepare_flags<<<ew_grid(*c, n + m), kThreads, 0, c->stream>>>(b, n + m, tol, c->red, c->S);
+  c->launches++;
+  return 0;
+}
+
+int LinSys::solve_dev(double *b, const double *ws, int first_batch) {
+  Ctx &cx = *c;
+  DevScalars *S = cx.S;
+  const int *done = &S->cg_done;
+  const int gn = ew_grid(cx, n), gm = ew_grid(cx, m);
+  cudaStream_t st = cx.stream;
+  // tmp = R_y^-1 ry ; b[:n] += A' tmp
+  k_scale_ry<<<gm, kThreads, 0, st>>>(b + n, diag_r + n, tmp, m, done);
+  {
+    EpiRhs epi; epi.b = b;
+    ElemMul e{tmp};
+    row_kernel<ElemMul, ElemMul, EpiRhs, false>
+        <<<chAt.grid, kThreads, 0, st>>>(At, e, At, e, chAt.d, chAt.n, epi, cx.red, S, done);
+  }
+  cx.launches += 2; cx.spmv_calls++;
+  if (ws) {
+    launch_A_scaled(ws, tmp, done);
+    EpiG0 epi;
+    epi.b = b; epi.s = ws; epi.rx = diag_r; epi.M = M; epi.r = r; epi.z = z; epi.p = p;
+    ElemMul ea{tmp}, eb{ws};
+    if (hasP)
+      row_kernel<ElemMul, ElemMul, EpiG0, true>
+          <<<chAt.grid, kThreads, 0, st>>>(At, ea, P, eb, chAt.d, chAt.n, epi, cx.red, S, done);
+    else
+      row_kernel<ElemMul, ElemMul, EpiG0, false>
+          <<<chAt.grid, kThreads, 0, st>>>(At, ea, P, eb, chAt.d, chAt.n, epi, cx.red, S, done);
+    cx.launches++; cx.spmv_calls++;
+  } else {
+    k_cg_init_cold<<<gn, kThreads, 0, st>>>(b, M, r, z, p, n, cx.red, S);
+    cx.launches++;
+  }
+  const long long max_its = 10ll * n;  // private.c:299
+  int batch = first_batch > 0 ? first_batch : (last_its + 1 < 1 ? 1 : last_its + 1);
+  if (batch > 64) batch = 64;
+  long long enq = 0;
+  int its = 0;
+  for (;;) {
+    for (int k = 0; k < batch && enq < max_its; ++k, ++enq) {
+      launch_A_scaled(p, tmp, done);
+      launch_G(tmp, p, Gp, done);
+      k_cg_update<<<gn, kThreads, 0, st>>>(b, r, z, p, Gp, M, n, cx.red, S);
+      k_cg_pupdate<<<gn, kThreads, 0, st>>>(p, z, n, S);
+      cx.launches += 2;
+    }
+    if (cx.fetch_scalars()) return -1;
+    its = cx.S_host->cg_its;
+    if (cx.S_host->cg_done || enq >= max_its) break;
+    batch = batch < 32 ? batch * 2 : 64;
+  }
+  if (first_batch <= 0) last_its = its;
+  tot_cg_its += its;
+  // y = R_y^-1 (A x - ry), or everything zero
+  {
+    EpiY epi; epi.by = b + n; epi.ry = diag_r + n;
+    ElemMul e{b};
+    row_kernel<ElemMul, ElemMul, EpiY, false>
+        <<<chA.grid, kThreads, 0, st>>>(A, e, A, e, chA.d, chA.n, epi, cx.red, S, &S->zero_rhs);
+    k_zero_if<<<ew_grid(cx, n + m), kThreads, 0, st>>>(b, n + m, &S->zero_rhs);
+  }
+  cx.launches += 2; cx.spmv_calls++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200
+
+// ================================================================== plugin ABI (C) ====
+using namespace b200;
+
+struct SCS_LIN_SYS_WORK {
+  Ctx ctx;
+  LinSys ls;
+  double *b = nullptr, *s = nullptr;  // device staging: n+m, n
+};
+
+static thread_local int g_device = 0;
+
+extern "C" scs_int scs_b200_set_device(scs_int device) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) return -1;
+  g_device = device;
+  return 0;
+}
+extern "C" scs_int scs_b200_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) return 0;
+  return cnt;
+}
+namespace b200 { int current_device() { return g_device; } }
+
+extern "C" const char *scs_get_lin_sys_method(void) { return "sparse-indirect-b200-pcg"; }
+
+extern "C" ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P, const scs_float *diag_r) {
+  if (!A || !diag_r) return nullptr;
+  SCS_LIN_SYS_WORK *w = new SCS_LIN_SYS_WORK();
+  if (w->ctx.init(g_device) || w->ls.init(&w->ctx, A, P)) {
+    scs_free_lin_sys_work(w);
+    return nullptr;
+  }
+  const int n = A->n, m = A->m;
+  w->ls.own_diag_r = true;
+  if (dev_alloc(&w->ls.diag_r, (size_t)n + m + 1) || dev_alloc(&w->b, (size_t)n + m) || dev_alloc(&w->s, (size_t)n) ||
+      h2d(w->ctx, w->ls.diag_r, diag_r, (size_t)n + m) || w->ls.update_precond() || w->ctx.sync()) {
+    scs_free_lin_sys_work(w);
+    return nullptr;
+  }
+  return w;
+}
+
+extern "C" void scs_free_lin_sys_work(ScsLinSysWork *w) {
+  if (!w) return;
+  cudaSetDevice(w->ctx.device);
+  cudaStreamSynchronize(w->ctx.stream);
+  w->ls.destroy();
+  dev_free(w->b);
+  dev_free(w->s);
+  w->ctx.destroy();
+  delete w;
+}
+
+extern "C" scs_int scs_solve_lin_sys(ScsLinSysWork *w, scs_float *b, const scs_float *s, scs_float tol) {
+  if (!w || !b) return -1;
+  Ctx &c = w->ctx;
+  if (cudaSetDevice(c.device) != cudaSuccess) return -1;
+  const int n = w->ls.n, m = w->ls.m;
+  if (tol <= 0.) B200_PRINTF("Warning: tol = %4f <= 0, likely compiled without setting INDIRECT flag.\n", tol);
+  if (h2d(c, w->b, b, (size_t)n + m)) return -1;
+  if (s && h2d(c, w->s, s, (size_t)n)) return -1;
+  if (w->ls.prepare_flags(w->b, tol)) return -1;
+  if (w->ls.solve_dev(w->b, s ? w->s : nullptr, s ? 0 : 16)) return -1;
+  if (d2h(c, b, w->b, (size_t)n + m) || c.sync()) return -1;
+  return 0;
+}
+
+extern "C" scs_int scs_update_lin_sys_diag_r(ScsLinSysWork *w, const scs_float *new_diag_r) {
+  if (!w || !new_diag_r) return -1;
+  Ctx &c = w->ctx;
+  if (cudaSetDevice(c.device) != cudaSuccess) return -1;
+  if (h2d(c, w->ls.diag_r, new_diag_r, (size_t)w->ls.n + w->ls.m) || w->ls.update_precond() || c.sync()) return -1;
+  return 0;
+}
+
+extern "C" scs_int scs_b200_lin_sys_cg_its(const ScsLinSysWork *w) { return w ? (scs_int)w->ls.tot_cg_its : 0; }
+
+// ------------------------------------------------------- SCS(accum_by_*) test surface --
+static int accum_generic(int rows_out, int cols_in, const ScsMatrix *Mh, bool transpose_first, bool sym_upper,
+                         const scs_float *x, scs_float *y) {
+  Ctx c;
+  if (c.init(g_device)) return -1;
+  CsrDev a, t;
+  ChunkList ch;
+  int rc = -1;
+  double *dx = nullptr, *dy = nullptr;
+  do {
+    if (sym_upper) {
+      if (csr_from_upper_csc(c, a, Mh->n, Mh->p, Mh->i, Mh->x)) break;
+    } else {
+      if (csr_upload(c, t, Mh->n, Mh->m, Mh->p, Mh->i, Mh->x)) break;  // CSR(M')
+      if (transpose_first) {
+        if (csr_transpose(c, t, a)) break;  // CSR(M)
+      } else {
+        a = t;
+        t = CsrDev();
+      }
+    }
+    if (chunks_build(c, ch, a, nullptr)) break;
+    if (dev_alloc(&dx, (size_t)cols_in) || dev_alloc(&dy, (size_t)rows_out)) break;
+    if (h2d(c, dx, x, (size_t)cols_in) || h2d(c, dy, y, (size_t)rows_out)) break;
+    EpiAccum epi; epi.y = dy;
+    ElemMul e{dx};
+    row_kernel<ElemMul, ElemMul, EpiAccum, false>
+        <<<ch.grid, kThreads, 0, c.stream>>>(a, e, a, e, ch.d, ch.n, epi, c.red, c.S, nullptr);
+    if (cudaGetLastError() != cudaSuccess) break;
+    if (d2h(c, y, dy, (size_t)rows_out) || c.sync()) break;
+    rc = 0;
+  } while (0);
+  csr_free(a);
+  csr_free(t);
+  chunks_free(ch);
+  dev_free(dx);
+  dev_free(dy);
+  c.destroy();
+  return rc;
+}
+
+extern "C" scs_int scs_b200_accum_by_a(const ScsMatrix *A, const scs_float *x, scs_float *y) {
+  if (!A || !x || !y) return -1;
+  return accum_generic(A->m, A->n, A, true, false, x, y);
+}
+extern "C" scs_int scs_b200_accum_by_atrans(const ScsMatrix *A, const scs_float *x, scs_float *y) {
+  if (!A || !x || !y) return -1;
+  return accum_generic(A->n, A->m, A, false, false, x, y);
+}
+extern "C" scs_int scs_b200_accum_by_p(const ScsMatrix *P, const scs_float *x, scs_float *y) {
+  if (!P || !x || !y) return -1;
+  return accum_generic(P->n, P->n, P, false, true, x, y);
+}

@@ -1,0 +1,52 @@
+// linsys.cuh -- device-resident quasi-definite KKT solve by preconditioned CG.
+//
+// Replaces S/linsys/cpu/indirect/private.c (the algorithmic template) and is NOT derived
+// from S/linsys/gpu/ (cuSPARSE/cuBLAS calls with a host sync per dot product).
+//
+//   [R_x + P   A' ] [x]   [rx]        x = (R_x + P + A' R_y^-1 A)^-1 (rx + A' R_y^-1 ry)
+//   [  A     -R_y ] [y] = [ry]   =>   y = R_y^-1 (A x - ry)                (private.c:266-275)
+//
+// All CG scalars (alpha, beta, z'r, ||r||_inf, the stop flag) live in DevScalars; kernels
+// launched after convergence return immediately, so the host only reads one flag per batch
+// of enqueued CG iterations.
+#pragma once
+#include "sparse.cuh"
+
+namespace b200 {
+
+struct LinSys {
+  Ctx *c = nullptr;
+  int n = 0, m = 0;
+  CsrDev A, At, P;  // CSR(A): m rows; CSR(A'): n rows; full symmetric CSR(P): n rows
+  bool hasP = false;
+  ChunkList chA, chAt;   // chAt is built over the fused (A', P) rows
+  double *diag_r = nullptr;  // n+m(+1) on device; owned iff own_diag_r
+  bool own_diag_r = false;
+  double *Pdiag = nullptr;  // n (zeros when !hasP)
+  double *M = nullptr, *p = nullptr, *r = nullptr, *Gp = nullptr, *z = nullptr;  // n
+  double *tmp = nullptr;                                                          // m
+  long long tot_cg_its = 0;
+  int last_its = 2;
+
+  // A (m x n) and P (n x n upper, may be null) are host CSC matrices.
+  int init(Ctx *ctx, const ScsMatrix *Ah, const ScsMatrix *Ph);
+  // build chunk lists and CG work vectors; call after the matrices have their final values
+  int finalize_structure();
+  void destroy();
+  int update_precond();  // M = 1 / diag(R_x + P + A' R_y^-1 A)   (private.c:50-84)
+  // b = [rx; ry] (device, n+m) -> [x; y] in place.  ws: warm start for x (device, n) or
+  // null.  Before the call the caller must have set S->cg_tol, S->zero_rhs and
+  // S->cg_done (= zero_rhs).  first_batch <= 0 picks the adaptive default.
+  int solve_dev(double *b, const double *ws, int first_batch);
+  // sets S->cg_tol = tol and the zero-rhs flags from ||b||_inf (device reduction)
+  int prepare_flags(const double *b, double tol);
+  // algorithmic bytes
+  double bytes_A() const { return 12.0 * A.nnz + 4.0 * (m + 1) + 8.0 * n + 8.0 * m; }
+  double bytes_At() const { return 12.0 * At.nnz + 4.0 * (n + 1) + 8.0 * m + 8.0 * n; }
+  double bytes_P() const { return hasP ? 12.0 * P.nnz + 4.0 * (n + 1) + 16.0 * n : 0.0; }
+  // launchers shared with the ADMM driver
+  int launch_A_scaled(const double *x, double *out, const int *skip);  // out = R_y^-1 A x
+  int launch_G(const double *zin, const double *pin, double *out, const int *skip);  // out = A'z + P p + R_x p ; S->alpha
+};
+
+}  // namespace b200

@@ -1,0 +1,1381 @@
+// scs_solver.cu -- device-resident ADMM loop behind the public SCS C API.
+//
+// Restates the host control flow of S/src/scs.c (scs_init / scs_update / scs_solve /
+// scs_finish, scs.c:1193-1496) around a loop body in which every vector lives in HBM:
+//
+//   k_prep      normalize_v + v_prev copy + RHS build + CG warm start + CG tolerance
+//               (scs.c:1315-1324, 696-719)
+//   LinSys      PCG (linsys.cu)
+//   k_rootplus  the five R-weighted dot products and the tau root (scs.c:667-688)
+//   k_pre       u_t -= tau g ; u = 2 u_t - v ; zero/nonneg cones fully, others pre-scaled
+//               (scs.c:727, 754-768 ; cones.c:1562-1571)
+//   ConeDev     box / SOC / PSD / exp / power kernels with the Moreau recombination fused
+//   k_post      rsk = R (v + u - 2 u_t) ; v += alpha (u - u_t) ; sum v^2 for the next
+//               normalize_v (scs.c:739-751)
+//   residuals   two SpMV passes with fat epilogues -> ~20 scalars, D2H every 25 iterations
+//               (scs.c:513-585, 465-509)
+//   AaDev       Anderson acceleration (aa.cu)
+//
+// Only the residual scalar block and one CG stop flag per iteration cross to the host.
+#include <chrono>
+#include <csignal>
+#include <string>
+
+#include "aa.cuh"
+#include "cones.cuh"
+#include "linsys.cuh"
+
+namespace b200 {
+
+int current_device();
+
+// ------------------------------------------------------------------ constants ---------
+// S/include/glbopts.h:35-50,184-257
+#define B200_SCS_VERSION "3.2.11"
+constexpr int kFeasibleIters = 1, kRescalingMinIters = 100, kConvergedInterval = 25, kPrintInterval = 250;
+constexpr double kDivEps = 1e-18, kTauFactor = 10.0, kInfeasNegTol = 1e-9;
+constexpr double kMaxScale = 1e6, kMinScale = 1e-6, kCgBestTol = 1e-12, kCgTolFactor = 0.2, kCgRate = 1.5;
+constexpr double kMinNormFactor = 1e-4, kMaxNormFactor = 1e4;
+constexpr int kRuizPasses = 25, kL2Passes = 1;
+constexpr double kAaSafeguard = 1.0, kAaMaxWeight = 1e10;
+constexpr int kAaIrSteps = 5;
+
+static inline double safediv_pos_h(double x, double y) { return y < kDivEps ? x / kDivEps : x / y; }
+
+static inline int ew_grid(const Ctx &c, long long len) {
+  long long g = (len + kThreads - 1) / kThreads;
+  if (g < 1) g = 1;
+  return (int)(g < c.grid_ew() ? g : c.grid_ew());
+}
+
+// ------------------------------------------------------------ SIGINT (ctrlc.c) --------
+static volatile sig_atomic_t g_int_detected = 0;
+static struct sigaction g_old_action;
+static int g_listener_depth = 0;
+static void b200_sigint_handler(int) { g_int_detected = 1; }
+static void start_interrupt_listener() {
+  if (g_listener_depth++ == 0) {
+    struct sigaction act;
+    g_int_detected = 0;
+    act.sa_flags = 0;
+    sigemptyset(&act.sa_mask);
+    act.sa_handler = b200_sigint_handler;
+    sigaction(SIGINT, &act, &g_old_action);
+  }
+}
+static void end_interrupt_listener() {
+  if (g_listener_depth > 0 && --g_listener_depth == 0) {
+    struct sigaction act;
+    sigaction(SIGINT, &g_old_action, &act);
+  }
+}
+
+// ------------------------------------------------------------------ kernels -----------
+// diag_r = [rho_x 1_n ; r_y ; TAU_FACTOR]   (scs.c:929-938, cones.c:349-363)
+__global__ void __launch_bounds__(kThreads)
+k_set_diag_r(double *__restrict__ R, int n, int m, int z, double rho_x, double scale) {
+  const int l = n + m + 1;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x) {
+    double v;
+    if (j < n) v = rho_x;
+    else if (j < n + z) v = 1.0 / (1000.0 * scale);
+    else if (j < n + m) v = 1.0 / scale;
+    else v = kTauFactor;
+    R[j] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_fill(double *__restrict__ x, double v, long long len) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < len; j += (long long)gridDim.x * blockDim.x)
+    x[j] = v;
+}
+
+// x <- 1 / sqrt(limit(pre(x)))  (apply_limit + SQRTF + SAFEDIV_POS, scs_matrix.c:203-208,235-236)
+__global__ void __launch_bounds__(kThreads) k_inv_sqrt_limit(double *__restrict__ x, int len, int pre_sqrt) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) {
+    double v = x[j];
+    if (pre_sqrt) v = sqrt(v);
+    v = v < kMinNormFactor ? 1.0 : v;
+    v = v > kMaxNormFactor ? kMaxNormFactor : v;
+    v = sqrt(v);
+    x[j] = v < kDivEps ? 1.0 / kDivEps : 1.0 / v;
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_sqrt(double *__restrict__ x, int len) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) x[j] = sqrt(x[j]);
+}
+__global__ void __launch_bounds__(kThreads)
+k_mul_inplace(double *__restrict__ a, const double *__restrict__ b, int len) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) a[j] *= b[j];
+}
+
+// rescale functors (scs_matrix.c:344-364): the same expression on both copies of A
+struct RescaleA {   // CSR(A): row = i, col = j
+  const double *Dt, *Et;
+  __device__ __forceinline__ double operator()(int row, int col, double v) const { return v * (Dt[row] * Et[col]); }
+};
+struct RescaleAt {  // CSR(A'): row = j, col = i
+  const double *Dt, *Et;
+  __device__ __forceinline__ double operator()(int row, int col, double v) const { return v * (Dt[col] * Et[row]); }
+};
+struct RescaleP {
+  const double *Et;
+  __device__ __forceinline__ double operator()(int row, int col, double v) const { return v * (Et[row] * Et[col]); }
+};
+// Ruiz / L2 column pass over (A', P): separate accumulators are not needed, max and sum
+// of squares both combine across the two matrices
+struct EpiStoreComb : EpiNoState {
+  double *y;
+  __device__ __forceinline__ void row(State &, int r, double acc) const { y[r] = acc; }
+};
+
+// b *= D ; c *= E ; sigma from the inf-norms (normalize.c:33-52)
+__global__ void __launch_bounds__(kThreads)
+k_scale_bc(double *__restrict__ b, const double *__restrict__ D, int m, double *__restrict__ c,
+           const double *__restrict__ E, int n, RedWs ws, DevScalars *S) {
+  double v[2] = {0.0, 0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m + n; j += gridDim.x * blockDim.x) {
+    if (j < m) {
+      const double t = b[j] * D[j];
+      b[j] = t;
+      v[0] = fmax(v[0], fabs(t));
+    } else {
+      const double t = c[j - m] * E[j - m];
+      c[j - m] = t;
+      v[1] = fmax(v[1], fabs(t));
+    }
+  }
+  grid_reduce<0, 2>(v, ws, [S](double *o) {
+    double sigma = fmax(o[0], o[1]);
+    sigma = sigma < kMinNormFactor ? 1.0 : sigma;
+    sigma = sigma > kMaxNormFactor ? kMaxNormFactor : sigma;
+    S->sigma = sigma < kDivEps ? 1.0 / kDivEps : 1.0 / sigma;
+  });
+}
+__global__ void __launch_bounds__(kThreads)
+k_scale_sigma(double *__restrict__ b, int m, double *__restrict__ c, int n, const DevScalars *S) {
+  const double sg = S->sigma;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m + n; j += gridDim.x * blockDim.x) {
+    if (j < m) b[j] *= sg; else c[j - m] *= sg;
+  }
+}
+
+// g = [c ; -b]   (scs.c:1066-1074)
+__global__ void __launch_bounds__(kThreads)
+k_build_g(double *__restrict__ g, const double *__restrict__ c, const double *__restrict__ b, int n, int m) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n + m; j += gridDim.x * blockDim.x)
+    g[j] = j < n ? c[j] : -b[j - n];
+}
+
+// cold start v = [0 ; 0 ; 1]  (scs.c:659-663)
+__global__ void __launch_bounds__(kThreads) k_cold_start(double *__restrict__ v, int l) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x) v[j] = (j == l - 1) ? 1.0 : 0.0;
+}
+// warm start v = [x ; y + s / R_y ; 1] after normalising (x,y,s)  (scs.c:638-657, normalize.c:64-76)
+__global__ void __launch_bounds__(kThreads)
+k_warm_start(double *__restrict__ v, const double *__restrict__ x, const double *__restrict__ y,
+             const double *__restrict__ s, const double *__restrict__ D, const double *__restrict__ E,
+             const double *__restrict__ R, int n, int m, double primal_scale, double dual_scale) {
+  const int l = n + m + 1;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x) {
+    double val;
+    if (j < n) {
+      val = x[j] / (E[j] / dual_scale);
+    } else if (j < n + m) {
+      const int i = j - n;
+      const double yn = y[i] / (D[i] / primal_scale);
+      const double sn = s[i] * (D[i] * dual_scale);
+      val = yn + sn / R[j];
+    } else {
+      val = 1.0;
+    }
+    v[j] = (val != val) ? 0.0 : val;
+  }
+}
+
+// normalize_v, v_prev copy, RHS, warm start, CG tolerance and flags
+template <bool ACCEL>
+__global__ void __launch_bounds__(kThreads)
+k_prep(double *__restrict__ v, double *__restrict__ v_prev, double *__restrict__ u_t, const double *__restrict__ u,
+       const double *__restrict__ g, const double *__restrict__ R, double *__restrict__ ws, int n, int m, int it,
+       RedWs red, DevScalars *S) {
+  const int l = n + m + 1;
+  double sc = 1.0;
+  if (it >= kFeasibleIters) {
+    const double vn = sqrt(S->vnorm2);
+    if (vn != 0.0) sc = sqrt((double)l) / vn;  // ITERATE_NORM == 1
+  }
+  const double tau_u = u[l - 1];
+  double mx[2] = {0.0, 0.0};  // ||ws||_inf, ||rhs||_inf
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x) {
+    const double vj = v[j] * sc;
+    v[j] = vj;
+    if (ACCEL) v_prev[j] = vj;
+    if (j < n) {
+      const double ut = vj * R[j];
+      u_t[j] = ut;
+      const double w = fma(tau_u, g[j], u[j]);
+      ws[j] = w;
+      mx[0] = fmax(mx[0], fabs(w));
+      mx[1] = fmax(mx[1], fabs(ut));
+    } else if (j < l - 1) {
+      const double ut = -vj * R[j];
+      u_t[j] = ut;
+      mx[1] = fmax(mx[1], fabs(ut));
+    } else {
+      u_t[j] = vj;
+    }
+  }
+  grid_reduce<0, 2>(mx, red, [S, it](double *o) {
+    double tol = fmin(S->nm_ax_s_btau, S->nm_px_aty_ctau);
+    const double nm_ws = o[0] / pow((double)it + 1.0, kCgRate);
+    tol = kCgTolFactor * fmin(tol, nm_ws);
+    S->cg_tol = fmax(kCgBestTol, tol);
+    S->zero_rhs = (o[1] <= 1e-12) ? 1 : 0;
+    S->cg_done = S->zero_rhs;
+    S->cg_its = 0;
+  });
+}
+
+// root_plus (scs.c:667-688): p = u_t (after the solve), mu = v, eta = v[l-1]
+__global__ void __launch_bounds__(kThreads)
+k_rootplus(const double *__restrict__ u_t, const double *__restrict__ v, const double *__restrict__ g,
+           const double *__restrict__ R, int nm, int it, RedWs red, DevScalars *S) {
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nm; j += gridDim.x * blockDim.x) {
+    const double ri = R[j], gi = g[j], pi = u_t[j], mui = v[j];
+    s[0] = fma(gi * gi, ri, s[0]);
+    s[1] = fma(mui * gi, ri, s[1]);
+    s[2] = fma(pi * gi, ri, s[2]);
+    s[3] = fma(pi * pi, ri, s[3]);
+    s[4] = fma(pi * mui, ri, s[4]);
+  }
+  const double eta = v[nm], tau_scale = R[nm];
+  grid_reduce<5, 0>(s, red, [S, it, eta, tau_scale](double *o) {
+    if (it < kFeasibleIters) {
+      S->tau = 1.0;
+    } else {
+      const double a = tau_scale + o[0];
+      const double b = o[1] - 2 * o[2] - eta * tau_scale;
+      const double c = o[3] - o[4];
+      const double rad = b * b - 4 * a * c;
+      S->tau = (-b + sqrt(fmax(rad, 0.0))) / (2 * a);
+    }
+  });
+}
+
+// u_t -= tau g ; u = 2 u_t - v ; zero / nonneg rows done, other rows pre-scaled by -R with
+// s saved in rsk (scratch until k_post overwrites it)
+__global__ void __launch_bounds__(kThreads)
+k_pre(double *__restrict__ u_t, double *__restrict__ u, double *__restrict__ rsk, const double *__restrict__ v,
+      const double *__restrict__ g, const double *__restrict__ R, int n, int m, int z, int zl, int it,
+      const DevScalars *S) {
+  const int l = n + m + 1;
+  const double tau = S->tau;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x) {
+    const double ut = (j < l - 1) ? fma(-tau, g[j], u_t[j]) : tau;
+    u_t[j] = ut;
+    const double s = 2 * ut - v[j];
+    double out;
+    if (j < n) {
+      out = s;
+    } else if (j < l - 1) {
+      const int row = j - n;
+      if (row < zl) {
+        out = zl_moreau(row, z, s, R[j]);
+      } else {
+        out = -R[j] * s;
+        rsk[j] = s;
+      }
+    } else {
+      out = (it < kFeasibleIters) ? 1.0 : fmax(s, 0.0);
+    }
+    u[j] = out;
+  }
+}
+
+// MODE 0: rsk and dual step ; 1: rsk only ; 2: dual step only   (scs.c:739-751)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_post(double *__restrict__ v, double *__restrict__ rsk, const double *__restrict__ u, const double *__restrict__ u_t,
+       const double *__restrict__ R, int l, double alpha, RedWs red, DevScalars *S) {
+  double s[1] = {0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x) {
+    const double vj = v[j], uj = u[j], utj = u_t[j];
+    if (MODE != 2) rsk[j] = (vj + uj - 2 * utj) * R[j];
+    if (MODE != 1) {
+      const double vn = fma(alpha, uj - utj, vj);
+      v[j] = vn;
+      s[0] = fma(vn, vn, s[0]);
+    }
+  }
+  if (MODE != 1) grid_reduce<1, 0>(s, red, [S](double *o) { S->vnorm2 = o[0]; });
+}
+
+// v <- rsk / R+ + 2 u_t - u after a scale update (scs.c:1180-1186)
+__global__ void __launch_bounds__(kThreads)
+k_remap_v(double *__restrict__ v, const double *__restrict__ rsk, const double *__restrict__ u,
+          const double *__restrict__ u_t, const double *__restrict__ R, int l) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x)
+    v[j] = rsk[j] / R[j] + 2 * u_t[j] - u[j];
+}
+
+// ---- residual epilogues (scs.c:513-585 and 465-509) ----
+// primal pass over CSR(A), gather x = u[0:n]
+struct EpiResA {
+  static constexpr bool kSeparate = false;
+  struct State { double bty, m[7]; };
+  const double *u, *rsk, *b, *D;
+  int n, m_;
+  double inv_ds, dual_scale;
+  __device__ __forceinline__ void row2(State &, int, double, double) const {}
+  __device__ __forceinline__ void init(State &s) const {
+    s.bty = 0.0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) s.m[k] = 0.0;
+  }
+  __device__ __forceinline__ void row(State &st, int i, double ax) const {
+    const double tau = fabs(u[n + m_]);
+    const double s = rsk[n + i], bi = b[i], yi = u[n + i], Di = D[i];
+    const double axs = ax + s;
+    const double axsb = axs - tau * bi;
+    const double f = inv_ds / Di;
+    st.bty = fma(yi, bi, st.bty);
+    st.m[0] = fmax(st.m[0], fabs(axsb));
+    st.m[1] = fmax(st.m[1], fabs(axs));
+    st.m[2] = fmax(st.m[2], fabs(ax));
+    st.m[3] = fmax(st.m[3], fabs(axsb * f));
+    st.m[4] = fmax(st.m[4], fabs(axs * f));
+    st.m[5] = fmax(st.m[5], fabs(ax * f));
+    st.m[6] = fmax(st.m[6], fabs(s / (Di * dual_scale)));
+  }
+  __device__ __forceinline__ void finish(State &st, const RedWs &ws, DevScalars *S) const {
+    double v[8] = {st.bty, st.m[0], st.m[1], st.m[2], st.m[3], st.m[4], st.m[5], st.m[6]};
+    const double *uu = u, *rr = rsk;
+    const int l1 = n + m_;
+    grid_reduce<1, 7>(v, ws, [S, uu, rr, l1](double *o) {
+      S->res[R_TAU] = fabs(uu[l1]);
+      S->res[R_KAP] = fabs(rr[l1]);
+      S->res[R_BTY_TAU] = o[0];
+      S->res[R_NM_AX_S_BTAU] = o[1];
+      S->res[R_NM_AX_S] = o[2];
+      S->res[R_NM_AX] = o[3];
+      S->res[R_ONM_AX_S_BTAU] = o[4];
+      S->res[R_ONM_AX_S] = o[5];
+      S->res[R_ONM_AX] = o[6];
+      S->res[R_ONM_S] = o[7];
+      S->nm_ax_s_btau = o[1];
+    });
+  }
+};
+// dual pass over (CSR(A'), CSR(P)), gathers y = u[n:] and x = u[0:n]
+struct EpiResAt {
+  static constexpr bool kSeparate = true;
+  struct State { double xpx, ctx, m[6]; };
+  const double *u, *c, *E;
+  int n, m_;
+  double inv_ps;
+  __device__ __forceinline__ void init(State &s) const {
+    s.xpx = 0.0; s.ctx = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s.m[k] = 0.0;
+  }
+  __device__ __forceinline__ void row(State &st, int j, double aty) const { row2(st, j, aty, 0.0); }
+  __device__ __forceinline__ void row2(State &st, int j, double aty, double px) const {
+    const double tau = fabs(u[n + m_]);
+    const double xj = u[j], cj = c[j];
+    const double pac = px + aty + tau * cj;
+    const double f = inv_ps / E[j];
+    st.xpx = fma(px, xj, st.xpx);
+    st.ctx = fma(xj, cj, st.ctx);
+    st.m[0] = fmax(st.m[0], fabs(pac));
+    st.m[1] = fmax(st.m[1], fabs(px));
+    st.m[2] = fmax(st.m[2], fabs(aty));
+    st.m[3] = fmax(st.m[3], fabs(pac * f));
+    st.m[4] = fmax(st.m[4], fabs(px * f));
+    st.m[5] = fmax(st.m[5], fabs(aty * f));
+  }
+  __device__ __forceinline__ void finish(State &st, const RedWs &ws, DevScalars *S) const {
+    double v[8] = {st.xpx, st.ctx, st.m[0], st.m[1], st.m[2], st.m[3], st.m[4], st.m[5]};
+    grid_reduce<2, 6>(v, ws, [S](double *o) {
+      S->res[R_XPX_TAU] = o[0];
+      S->res[R_CTX_TAU] = o[1];
+      S->res[R_NM_PX_ATY_CTAU] = o[2];
+      S->res[R_NM_PX] = o[3];
+      S->res[R_NM_ATY] = o[4];
+      S->res[R_ONM_PX_ATY_CTAU] = o[5];
+      S->res[R_ONM_PX] = o[6];
+      S->res[R_ONM_ATY] = o[7];
+      S->nm_px_aty_ctau = o[2];
+    });
+  }
+};
+
+// un-normalised solution (normalize.c:78-90) + ||s||_inf, ||y||_inf, s'y (scs.c:885-887)
+__global__ void __launch_bounds__(kThreads)
+k_finalize_sol(double *__restrict__ xo, double *__restrict__ yo, double *__restrict__ so, const double *__restrict__ u,
+               const double *__restrict__ rsk, const double *__restrict__ D, const double *__restrict__ E, int n, int m,
+               double primal_scale, double dual_scale, RedWs red, DevScalars *S) {
+  double v[3] = {0.0, 0.0, 0.0};  // s'y | max s, max y
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n + m; j += gridDim.x * blockDim.x) {
+    if (j < n) {
+      xo[j] = u[j] * (E[j] / dual_scale);
+    } else {
+      const int i = j - n;
+      const double y = u[j] * (D[i] / primal_scale);
+      const double s = rsk[j] / (D[i] * dual_scale);
+      yo[i] = y;
+      so[i] = s;
+      v[0] = fma(s, y, v[0]);
+      v[1] = fmax(v[1], fabs(s));
+      v[2] = fmax(v[2], fabs(y));
+    }
+  }
+  grid_reduce<1, 2>(v, red, [S](double *o) {
+    S->fin[2] = o[0];
+    S->fin[0] = o[1];
+    S->fin[1] = o[2];
+  });
+}
+__global__ void __launch_bounds__(kThreads)
+k_scale3(double *__restrict__ x, int n, double fx, double *__restrict__ y, double *__restrict__ s, int m, double fy,
+         double fs) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n + m; j += gridDim.x * blockDim.x) {
+    if (j < n) x[j] *= fx;
+    else { y[j - n] *= fy; s[j - n] *= fs; }
+  }
+}
+
+// ---------------------------------------------------------- host-side structures -------
+struct HostResid {  // ScsResiduals scalars (scs_work.h:29-50); vectors are reduced on the device
+  int last_iter = -1;
+  double xt_p_x = 0, xt_p_x_tau = 0, ctx = 0, ctx_tau = 0, bty = 0, bty_tau = 0, pobj = 0, dobj = 0, gap = 0;
+  double tau = 0, kap = 0, res_pri = 0, res_dual = 0, res_infeas = NAN, res_unbdd_p = NAN, res_unbdd_a = NAN;
+  double nm_ax_s_btau = 0, nm_ax_s = 0, nm_ax = 0, nm_px_aty_ctau = 0, nm_px = 0, nm_aty = 0, nm_s = 0;
+};
+
+// compute_residuals, scs.c:441-463
+static void compute_residuals_h(HostResid &r, double pd) {
+  const double tol = kInfeasNegTol / pd;
+  r.res_pri = safediv_pos_h(r.nm_ax_s_btau, r.tau);
+  r.res_dual = safediv_pos_h(r.nm_px_aty_ctau, r.tau);
+  r.res_unbdd_a = NAN; r.res_unbdd_p = NAN; r.res_infeas = NAN;
+  if (r.ctx_tau < -tol) {
+    r.res_unbdd_a = safediv_pos_h(r.nm_ax_s, -r.ctx_tau);
+    r.res_unbdd_p = safediv_pos_h(r.nm_px, -r.ctx_tau);
+  }
+  if (r.bty_tau < -tol) r.res_infeas = safediv_pos_h(r.nm_aty, -r.bty_tau);
+}
+
+struct EventAccum {  // CUDA-event phase timers for info.{lin_sys,cone,accel}_time
+  static constexpr int kSlots = 48;
+  cudaEvent_t a[kSlots], b[kSlots];
+  int cat[kSlots];
+  int used = 0;
+  double total[3] = {0, 0, 0};
+  bool ok = false;
+  int init() {
+    for (int i = 0; i < kSlots; ++i) {
+      CUDA_OK(cudaEventCreate(&a[i]));
+      CUDA_OK(cudaEventCreate(&b[i]));
+    }
+    ok = true;
+    return 0;
+  }
+  void destroy() {
+    if (!ok) return;
+    for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(a[i]); cudaEventDestroy(b[i]); }
+    ok = false;
+  }
+  // the caller guarantees the stream has been synchronised after the recorded events
+  void flush() {
+    for (int i = 0; i < used; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, a[i], b[i]) == cudaSuccess) total[cat[i]] += ms;
+    }
+    used = 0;
+  }
+  int begin(int category, cudaStream_t st) {
+    if (used >= kSlots) return -1;
+    cat[used] = category;
+    cudaEventRecord(a[used], st);
+    return used;
+  }
+  void end(int slot, cudaStream_t st) {
+    if (slot < 0) return;
+    cudaEventRecord(b[slot], st);
+    used = slot + 1;
+  }
+  void reset() { used = 0; total[0] = total[1] = total[2] = 0; }
+};
+
+}  // namespace b200
+
+using namespace b200;
+
+struct SCS_WORK {
+  Ctx c;
+  LinSys ls;
+  ConeDev cone;
+  AaDev aa;
+  bool has_aa = false;
+  EventAccum ev;
+  int n = 0, m = 0, l = 0;
+  ScsSettings stgs;
+  std::string write_fn, csv_fn;
+  // device state
+  double *u = nullptr, *u_t = nullptr, *v = nullptr, *v_prev = nullptr, *rsk = nullptr, *g = nullptr;
+  double *diag_r = nullptr, *b = nullptr, *cvec = nullptr, *D = nullptr, *E = nullptr, *ws = nullptr;
+  double *sol_x = nullptr, *sol_y = nullptr, *sol_s = nullptr;
+  // host
+  std::vector<double> b_orig, c_orig;
+  double nm_b_orig = 0, nm_c_orig = 0, primal_scale = 1, dual_scale = 1;
+  HostResid r_n, r_o;
+  double setup_time = 0;
+  int time_limit_reached = 0;
+  double sum_log_scale_factor = 0;
+  int last_scale_update_iter = 0, n_log_scale_factor = 0, scale_updates = 0;
+  long long admm_iters = 0;
+  double alg_bytes = 0;
+};
+
+namespace b200 {
+
+using Clock = std::chrono::steady_clock;
+static inline double ms_since(const Clock::time_point &t0) {
+  return std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+}
+
+// ------------------------------------------------------------------ validation --------
+static int validate(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {  // scs.c:364-429
+  if (d->m <= 0 || d->n <= 0) {
+    B200_PRINTF("m and n must both be greater than 0; m = %li, n = %li\n", (long)d->m, (long)d->n);
+    return -1;
+  }
+  const ScsMatrix *A = d->A, *P = d->P;  // validate_lin_sys, scs_matrix.c:65-131
+  if (!A) { B200_PRINTF("A matrix missing\n"); return -1; }
+  if (!A->x || !A->i || !A->p) { B200_PRINTF("data incompletely specified\n"); return -1; }
+  if (A->m != d->m || A->n != d->n) { B200_PRINTF("A dimensions inconsistent with m, n\n"); return -1; }
+  const long long Anz = A->p[A->n];
+  if (((double)Anz / A->m > A->n) || Anz < 0) {
+    B200_PRINTF("Anz (nonzeros in A) = %li, outside of valid range\n", (long)Anz);
+    return -1;
+  }
+  int r_max = 0;
+  for (long long i = 0; i < Anz; ++i) {
+    if (A->i[i] > r_max) r_max = A->i[i];
+    if (A->i[i] < 0) { B200_PRINTF("negative row index in A\n"); return -1; }
+  }
+  if (r_max > A->m - 1) { B200_PRINTF("number of rows in A inconsistent with input dimension\n"); return -1; }
+  if (P) {
+    if (!P->x || !P->i || !P->p) { B200_PRINTF("P matrix incompletely specified\n"); return -1; }
+    if (P->n != A->n) { B200_PRINTF("P dimension = %li, inconsistent with n = %li\n", (long)P->n, (long)A->n); return -1; }
+    if (P->m != P->n) { B200_PRINTF("P is not square\n"); return -1; }
+    for (int j = 0; j < P->n; ++j)
+      for (int i = P->p[j]; i < P->p[j + 1]; ++i)
+        if (P->i[i] > j) { B200_PRINTF("P is not upper triangular\n"); return -1; }
+  }
+  // validate_cones, cones.c:583-755
+  if (k->z < 0) { B200_PRINTF("free cone dimension error\n"); return -1; }
+  if (k->l < 0) { B200_PRINTF("lp cone dimension error\n"); return -1; }
+  if (k->bsize < 0) { B200_PRINTF("box cone dimension error\n"); return -1; }
+  if (k->bsize > 1) {
+    if (!k->bl || !k->bu) { B200_PRINTF("box cone bounds missing\n"); return -1; }
+    for (int i = 0; i < k->bsize - 1; ++i)
+      if (k->bl[i] > k->bu[i]) { B200_PRINTF("infeasible: box lower bound larger than upper bound\n"); return -1; }
+  }
+  long long dims = (long long)k->z + k->l + k->bsize;
+  if (k->qsize < 0 || (k->qsize > 0 && !k->q)) { B200_PRINTF("soc cone dimension error\n"); return -1; }
+  for (int i = 0; i < k->qsize; ++i) {
+    if (k->q[i] < 0) { B200_PRINTF("soc cone dimension error\n"); return -1; }
+    dims += k->q[i];
+  }
+  if (k->ssize < 0 || (k->ssize > 0 && !k->s)) { B200_PRINTF("sd cone dimension error\n"); return -1; }
+  for (int i = 0; i < k->ssize; ++i) {
+    if (k->s[i] < 0) { B200_PRINTF("sd cone dimension error\n"); return -1; }
+    dims += (long long)k->s[i] * (k->s[i] + 1) / 2;
+  }
+  if (k->cssize < 0 || (k->cssize > 0 && !k->cs)) { B200_PRINTF("complex psd cone dimension error\n"); return -1; }
+  for (int i = 0; i < k->cssize; ++i) {
+    if (k->cs[i] < 0) { B200_PRINTF("complex psd cone dimension error\n"); return -1; }
+    dims += (long long)k->cs[i] * k->cs[i];
+  }
+  if (k->ed < 0) { B200_PRINTF("ed cone dimension error\n"); return -1; }
+  if (k->ep < 0) { B200_PRINTF("ep cone dimension error\n"); return -1; }
+  if (k->psize < 0 || (k->psize > 0 && !k->p)) { B200_PRINTF("power cone dimension error\n"); return -1; }
+  for (int i = 0; i < k->psize; ++i)
+    if (k->p[i] < -1 || k->p[i] > 1) { B200_PRINTF("power cone error, values must be in [-1,1]\n"); return -1; }
+  dims += 3ll * (k->ed + k->ep + k->psize);
+  if (dims != d->m) {
+    B200_PRINTF("Error: Cone dims %li != rows in A %li\n", (long)dims, (long)d->m);
+    return -1;
+  }
+  if (stgs->max_iters <= 0) { B200_PRINTF("max_iters must be positive\n"); return -1; }
+  if (stgs->eps_abs < 0) { B200_PRINTF("eps_abs tolerance must be positive\n"); return -1; }
+  if (stgs->eps_rel < 0) { B200_PRINTF("eps_rel tolerance must be positive\n"); return -1; }
+  if (stgs->eps_infeas < 0) { B200_PRINTF("eps_infeas tolerance must be positive\n"); return -1; }
+  if (stgs->alpha <= 0 || stgs->alpha >= 2) { B200_PRINTF("alpha must be in (0,2)\n"); return -1; }
+  if (stgs->rho_x <= 0) { B200_PRINTF("rho_x must be positive (1e-3 works well).\n"); return -1; }
+  if (stgs->scale <= 0) { B200_PRINTF("scale must be positive (1 works well).\n"); return -1; }
+  if (stgs->acceleration_interval <= 0) { B200_PRINTF("acceleration_interval must be positive (10 works well).\n"); return -1; }
+  if (stgs->acceleration_lookback < 0) {
+    B200_PRINTF("acceleration_lookback must be nonnegative (use acceleration_type_1=0 for type-II AA).\n");
+    return -1;
+  }
+  if (!std::isfinite(stgs->acceleration_regularization) || stgs->acceleration_regularization < 0) {
+    B200_PRINTF("acceleration_regularization must be a nonnegative finite number.\n");
+    return -1;
+  }
+  if (!std::isfinite(stgs->acceleration_relaxation) || stgs->acceleration_relaxation < 0 ||
+      stgs->acceleration_relaxation > 2) {
+    B200_PRINTF("acceleration_relaxation must be in [0, 2].\n");
+    return -1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ printing ----------
+static void print_line() {
+  char buf[68];
+  memset(buf, '-', 66);
+  buf[66] = '\n';
+  buf[67] = 0;
+  B200_PRINTF("%s", buf);
+}
+
+static void print_init_header(const ScsData *d, const ScsCone *k, const ScsSettings *s) {  // scs.c:123-177
+  print_line();
+  B200_PRINTF("\t       SCS v%s - Splitting Conic Solver\n\t(c) Brendan O'Donoghue, Stanford University, 2012\n",
+              B200_SCS_VERSION);
+  print_line();
+  B200_PRINTF("problem:  variables n: %i, constraints m: %i\n", (int)d->n, (int)d->m);
+  B200_PRINTF("cones: ");
+  if (k->z) B200_PRINTF("\t  z: primal zero / dual free vars: %li\n", (long)k->z);
+  if (k->l) B200_PRINTF("\t  l: linear vars: %li\n", (long)k->l);
+  if (k->bsize) B200_PRINTF("\t  b: box cone vars: %li\n", (long)k->bsize);
+  if (k->qsize) {
+    long tot = 0;
+    for (int i = 0; i < k->qsize; ++i) tot += k->q[i];
+    B200_PRINTF("\t  q: soc vars: %li, qsize: %li\n", tot, (long)k->qsize);
+  }
+  if (k->ssize) {
+    long tot = 0;
+    for (int i = 0; i < k->ssize; ++i) tot += (long)k->s[i] * (k->s[i] + 1) / 2;
+    B200_PRINTF("\t  s: psd vars: %li, ssize: %li\n", tot, (long)k->ssize);
+  }
+  if (k->cssize) {
+    long tot = 0;
+    for (int i = 0; i < k->cssize; ++i) tot += (long)k->cs[i] * k->cs[i];
+    B200_PRINTF("\t  cs: complex psd vars: %li, ssize: %li\n", tot, (long)k->cssize);
+  }
+  if (k->ep || k->ed) B200_PRINTF("\t  e: exp vars: %li, dual exp vars: %li\n", 3l * k->ep, 3l * k->ed);
+  if (k->psize) B200_PRINTF("\t  p: primal + dual power vars: %li\n", 3l * k->psize);
+  B200_PRINTF("settings: eps_abs: %.1e, eps_rel: %.1e, eps_infeas: %.1e\n"
+              "\t  alpha: %.2f, scale: %.2e, adaptive_scale: %i\n"
+              "\t  max_iters: %i, normalize: %i, rho_x: %.2e\n",
+              s->eps_abs, s->eps_rel, s->eps_infeas, s->alpha, s->scale, (int)s->adaptive_scale, (int)s->max_iters,
+              (int)s->normalize, s->rho_x);
+  if (s->acceleration_lookback != 0)
+    B200_PRINTF("\t  acceleration_lookback: %i, acceleration_interval: %i\n", (int)s->acceleration_lookback,
+                (int)s->acceleration_interval);
+  if (s->time_limit_secs) B200_PRINTF("\t  time_limit_secs: %.2e\n", s->time_limit_secs);
+  B200_PRINTF("lin-sys:  %s\n\t  nnz(A): %li, nnz(P): %li\n", scs_get_lin_sys_method(), (long)d->A->p[d->A->n],
+              d->P ? (long)d->P->p[d->P->n] : 0l);
+}
+
+static void print_header() {  // scs.c:179-196
+  print_line();
+  B200_PRINTF(" iter | pri res | dua res |   gap   |   obj   |  scale  | time (s)\n");
+  print_line();
+}
+
+static void print_summary(const SCS_WORK *w, int i, const Clock::time_point &t0) {  // scs.c:198-210
+  const HostResid &r = w->r_o;
+  B200_PRINTF("%*i|%*.2e %*.2e %*.2e %*.2e %*.2e %*.2e \n", 6, i, 9, r.res_pri, 9, r.res_dual, 9, r.gap, 9,
+              0.5 * (r.pobj + r.dobj), 9, w->stgs.scale, 9, (ms_since(t0) + w->setup_time) / 1e3);
+}
+
+static void print_footer(const ScsInfo *info) {  // scs.c:237-274
+  print_line();
+  B200_PRINTF("status:  %s\n", info->status);
+  B200_PRINTF("timings: total: %1.2es = setup: %1.2es + solve: %1.2es\n",
+              (info->setup_time + info->solve_time) / 1e3, info->setup_time / 1e3, info->solve_time / 1e3);
+  B200_PRINTF("\t lin-sys: %1.2es, cones: %1.2es, accel: %1.2es\n", info->lin_sys_time / 1e3, info->cone_time / 1e3,
+              info->accel_time / 1e3);
+  print_line();
+  B200_PRINTF("objective = %.6f", 0.5 * (info->pobj + info->dobj));
+  if (info->status_val == SCS_SOLVED_INACCURATE || info->status_val == SCS_UNBOUNDED_INACCURATE ||
+      info->status_val == SCS_INFEASIBLE_INACCURATE)
+    B200_PRINTF(" (inaccurate)");
+  B200_PRINTF("\n");
+  print_line();
+}
+
+// ------------------------------------------------------------------ setup pieces ------
+static int set_diag_r(SCS_WORK *w) {
+  k_set_diag_r<<<ew_grid(w->c, w->l), kThreads, 0, w->c.stream>>>(w->diag_r, w->n, w->m, w->cone.z, w->stgs.rho_x,
+                                                                  w->stgs.scale);
+  w->c.launches++;
+  return 0;
+}
+
+// SCS(normalize_a_p), scs_matrix.c:407-470, on the device copies of A, A', P
+static int normalize_a_p_dev(SCS_WORK *w) {
+  Ctx &c = w->c;
+  LinSys &ls = w->ls;
+  const int n = w->n, m = w->m;
+  cudaStream_t st = c.stream;
+  double *Dt = nullptr, *Et = nullptr;
+  if (dev_alloc(&Dt, (size_t)m) || dev_alloc(&Et, (size_t)n)) return -1;
+  k_fill<<<ew_grid(c, m), kThreads, 0, st>>>(w->D, 1.0, m);
+  k_fill<<<ew_grid(c, n), kThreads, 0, st>>>(w->E, 1.0, n);
+  c.launches += 2;
+  for (int pass = 0; pass < kRuizPasses + kL2Passes; ++pass) {
+    const bool l2 = pass >= kRuizPasses;
+    EpiStore eD; eD.y = Dt;
+    EpiStoreComb eE; eE.y = Et;
+    if (!l2) {
+      ElemAbsMax e;
+      row_kernel<ElemAbsMax, ElemAbsMax, EpiStore, false>
+          <<<ls.chA.grid, kThreads, 0, st>>>(ls.A, e, ls.A, e, ls.chA.d, ls.chA.n, eD, c.red, c.S, nullptr);
+      if (w->cone.enforce_boundaries(Dt, 0)) return -1;
+      k_inv_sqrt_limit<<<ew_grid(c, m), kThreads, 0, st>>>(Dt, m, 0);
+      if (ls.hasP)
+        row_kernel<ElemAbsMax, ElemAbsMax, EpiStoreComb, true>
+            <<<ls.chAt.grid, kThreads, 0, st>>>(ls.At, e, ls.P, e, ls.chAt.d, ls.chAt.n, eE, c.red, c.S, nullptr);
+      else
+        row_kernel<ElemAbsMax, ElemAbsMax, EpiStoreComb, false>
+            <<<ls.chAt.grid, kThreads, 0, st>>>(ls.At, e, ls.P, e, ls.chAt.d, ls.chAt.n, eE, c.red, c.S, nullptr);
+      k_inv_sqrt_limit<<<ew_grid(c, n), kThreads, 0, st>>>(Et, n, 0);
+      c.launches += 4;
+    } else {
+      ElemSumSq e;
+      row_kernel<ElemSumSq, ElemSumSq, EpiStore, false>
+          <<<ls.chA.grid, kThreads, 0, st>>>(ls.A, e, ls.A, e, ls.chA.d, ls.chA.n, eD, c.red, c.S, nullptr);
+      k_sqrt<<<ew_grid(c, m), kThreads, 0, st>>>(Dt, m);
+      if (w->cone.enforce_boundaries(Dt, 1)) return -1;
+      k_inv_sqrt_limit<<<ew_grid(c, m), kThreads, 0, st>>>(Dt, m, 0);
+      if (ls.hasP)
+        row_kernel<ElemSumSq, ElemSumSq, EpiStoreComb, true>
+            <<<ls.chAt.grid, kThreads, 0, st>>>(ls.At, e, ls.P, e, ls.chAt.d, ls.chAt.n, eE, c.red, c.S, nullptr);
+      else
+        row_kernel<ElemSumSq, ElemSumSq, EpiStoreComb, false>
+            <<<ls.chAt.grid, kThreads, 0, st>>>(ls.At, e, ls.P, e, ls.chAt.d, ls.chAt.n, eE, c.red, c.S, nullptr);
+      k_inv_sqrt_limit<<<ew_grid(c, n), kThreads, 0, st>>>(Et, n, 1);
+      c.launches += 5;
+    }
+    RescaleA ra{Dt, Et};
+    RescaleAt rat{Dt, Et};
+    row_map_kernel<<<ls.chA.grid, kThreads, 0, st>>>(ls.A, ls.chA.d, ls.chA.n, ra);
+    row_map_kernel<<<ls.chAt.grid, kThreads, 0, st>>>(ls.At, ls.chAt.d, ls.chAt.n, rat);
+    if (ls.hasP) {
+      RescaleP rp{Et};
+      row_map_kernel<<<ls.chAt.grid, kThreads, 0, st>>>(ls.P, ls.chAt.d, ls.chAt.n, rp);
+      c.launches++;
+    }
+    k_mul_inplace<<<ew_grid(c, m), kThreads, 0, st>>>(w->D, Dt, m);
+    k_mul_inplace<<<ew_grid(c, n), kThreads, 0, st>>>(w->E, Et, n);
+    c.launches += 4;
+  }
+  CUDA_OK(cudaGetLastError());
+  if (c.sync()) return -1;
+  dev_free(Dt);
+  dev_free(Et);
+  return 0;
+}
+
+// update_work_cache, scs.c:1066-1076: g = (R + M)^-1 [c ; -b] to CG_BEST_TOL
+static int update_work_cache(SCS_WORK *w) {
+  Ctx &c = w->c;
+  k_build_g<<<ew_grid(c, w->n + w->m), kThreads, 0, c.stream>>>(w->g, w->cvec, w->b, w->n, w->m);
+  c.launches++;
+  if (w->ls.prepare_flags(w->g, kCgBestTol)) return -1;
+  return w->ls.solve_dev(w->g, nullptr, 16);
+}
+
+// populate_residual_struct, scs.c:513-585 (+ unnormalize_residuals, scs.c:465-509)
+static int populate_residuals(SCS_WORK *w, int iter) {
+  if (w->r_n.last_iter == iter) return 0;
+  Ctx &c = w->c;
+  LinSys &ls = w->ls;
+  const int n = w->n, m = w->m;
+  {
+    EpiResA epi;
+    epi.u = w->u; epi.rsk = w->rsk; epi.b = w->b; epi.D = w->D; epi.n = n; epi.m_ = m;
+    epi.inv_ds = 1.0 / w->dual_scale; epi.dual_scale = w->dual_scale;
+    ElemMul e{w->u};
+    row_kernel<ElemMul, ElemMul, EpiResA, false>
+        <<<ls.chA.grid, kThreads, 0, c.stream>>>(ls.A, e, ls.A, e, ls.chA.d, ls.chA.n, epi, c.red, c.S, nullptr);
+  }
+  {
+    EpiResAt epi;
+    epi.u = w->u; epi.c = w->cvec; epi.E = w->E; epi.n = n; epi.m_ = m; epi.inv_ps = 1.0 / w->primal_scale;
+    ElemMul ea{w->u + n}, eb{w->u};
+    if (ls.hasP)
+      row_kernel<ElemMul, ElemMul, EpiResAt, true>
+          <<<ls.chAt.grid, kThreads, 0, c.stream>>>(ls.At, ea, ls.P, eb, ls.chAt.d, ls.chAt.n, epi, c.red, c.S, nullptr);
+    else
+      row_kernel<ElemMul, ElemMul, EpiResAt, false>
+          <<<ls.chAt.grid, kThreads, 0, c.stream>>>(ls.At, ea, ls.P, eb, ls.chAt.d, ls.chAt.n, epi, c.red, c.S, nullptr);
+  }
+  c.launches += 2; c.spmv_calls += 2;
+  CUDA_OK(cudaGetLastError());
+  if (c.fetch_scalars()) return -1;
+  w->ev.flush();
+  const double *R = c.S_host->res;
+  HostResid &r = w->r_n;
+  r.last_iter = iter;
+  r.tau = R[R_TAU]; r.kap = R[R_KAP];
+  r.xt_p_x_tau = ls.hasP ? R[R_XPX_TAU] : 0.0;
+  r.bty_tau = R[R_BTY_TAU]; r.ctx_tau = R[R_CTX_TAU];
+  r.bty = safediv_pos_h(r.bty_tau, r.tau);
+  r.ctx = safediv_pos_h(r.ctx_tau, r.tau);
+  r.xt_p_x = safediv_pos_h(r.xt_p_x_tau, r.tau * r.tau);
+  r.gap = fabs(r.xt_p_x + r.ctx + r.bty);
+  r.pobj = r.xt_p_x / 2. + r.ctx;
+  r.dobj = -r.xt_p_x / 2. - r.bty;
+  r.nm_ax_s_btau = R[R_NM_AX_S_BTAU]; r.nm_ax_s = R[R_NM_AX_S]; r.nm_ax = R[R_NM_AX];
+  r.nm_px_aty_ctau = R[R_NM_PX_ATY_CTAU]; r.nm_px = R[R_NM_PX]; r.nm_aty = R[R_NM_ATY];
+  r.nm_s = R[R_ONM_S];
+  compute_residuals_h(r, 1.0);
+  if (w->stgs.normalize) {
+    HostResid &o = w->r_o;
+    const double pd = w->primal_scale * w->dual_scale;
+    o.last_iter = r.last_iter; o.tau = r.tau;
+    o.kap = r.kap / pd; o.bty_tau = r.bty_tau / pd; o.ctx_tau = r.ctx_tau / pd; o.xt_p_x_tau = r.xt_p_x_tau / pd;
+    o.xt_p_x = r.xt_p_x / pd; o.ctx = r.ctx / pd; o.bty = r.bty / pd; o.pobj = r.pobj / pd; o.dobj = r.dobj / pd;
+    o.gap = r.gap / pd;
+    o.nm_ax_s_btau = R[R_ONM_AX_S_BTAU]; o.nm_ax_s = R[R_ONM_AX_S]; o.nm_ax = R[R_ONM_AX];
+    o.nm_px_aty_ctau = R[R_ONM_PX_ATY_CTAU]; o.nm_px = R[R_ONM_PX]; o.nm_aty = R[R_ONM_ATY];
+    o.nm_s = R[R_ONM_S];
+    compute_residuals_h(o, pd);
+  } else {
+    w->r_o = w->r_n;
+  }
+  return 0;
+}
+
+// has_converged, scs.c:589-627 (isless() == NaN-safe '<')
+static int has_converged(const SCS_WORK *w) {
+  const HostResid &r = w->r_o;
+  const double eps_abs = w->stgs.eps_abs, eps_rel = w->stgs.eps_rel, eps_infeas = w->stgs.eps_infeas;
+  if (r.tau > 0.) {
+    const double grl = fmax(fmax(fabs(r.xt_p_x), fabs(r.ctx)), fabs(r.bty));
+    const double prl = fmax(fmax(w->nm_b_orig * r.tau, r.nm_s), r.nm_ax) / r.tau;
+    const double drl = fmax(fmax(w->nm_c_orig * r.tau, r.nm_px), r.nm_aty) / r.tau;
+    if (std::isless(r.res_pri, eps_abs + eps_rel * prl) && std::isless(r.res_dual, eps_abs + eps_rel * drl) &&
+        std::isless(r.gap, eps_abs + eps_rel * grl))
+      return SCS_SOLVED;
+  }
+  if (std::isless(r.res_unbdd_a, eps_infeas) && std::isless(r.res_unbdd_p, eps_infeas)) return SCS_UNBOUNDED;
+  if (std::isless(r.res_infeas, eps_infeas)) return SCS_INFEASIBLE;
+  return 0;
+}
+
+// update_scale, scs.c:1112-1189
+static int update_scale(SCS_WORK *w, int iter) {
+  const HostResid &r = w->r_o;
+  const int since = iter - w->last_scale_update_iter;
+  double denom_pri = fmax(fmax(r.nm_ax, r.nm_s), w->nm_b_orig * r.tau);
+  double rel_pri = safediv_pos_h(r.nm_ax_s_btau, denom_pri);
+  double denom_dual = fmax(fmax(r.nm_px, r.nm_aty), w->nm_c_orig * r.tau);
+  double rel_dual = safediv_pos_h(r.nm_px_aty_ctau, denom_dual);
+  rel_pri = fmax(rel_pri, kDivEps);
+  rel_dual = fmax(rel_dual, kDivEps);
+  w->sum_log_scale_factor += log(rel_pri) - log(rel_dual);
+  w->n_log_scale_factor++;
+  const double factor = sqrt(exp(w->sum_log_scale_factor / (double)w->n_log_scale_factor));
+  if (since < kRescalingMinIters) return 0;
+  const double new_scale = fmin(fmax(w->stgs.scale * factor, kMinScale), kMaxScale);
+  if (new_scale == w->stgs.scale) return 0;
+  if (factor > sqrt(10.) || factor < 1. / sqrt(10.)) {
+    w->scale_updates++;
+    w->sum_log_scale_factor = 0;
+    w->n_log_scale_factor = 0;
+    w->last_scale_update_iter = iter;
+    w->stgs.scale = new_scale;
+    if (set_diag_r(w)) return -1;
+    if (w->ls.update_precond()) return -1;
+    if (update_work_cache(w)) return -1;
+    if (w->has_aa) w->aa.reset();
+    k_remap_v<<<ew_grid(w->c, w->l), kThreads, 0, w->c.stream>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, w->l);
+    w->c.launches++;
+  }
+  return 0;
+}
+
+static void free_work(SCS_WORK *w) {
+  if (!w) return;
+  cudaSetDevice(w->c.device);
+  if (w->c.stream) cudaStreamSynchronize(w->c.stream);
+  w->ls.destroy();
+  w->cone.destroy();
+  if (w->has_aa) w->aa.destroy();
+  w->ev.destroy();
+  dev_free(w->u); dev_free(w->u_t); dev_free(w->v); dev_free(w->v_prev); dev_free(w->rsk); dev_free(w->g);
+  dev_free(w->diag_r); dev_free(w->b); dev_free(w->cvec); dev_free(w->D); dev_free(w->E); dev_free(w->ws);
+  dev_free(w->sol_x); dev_free(w->sol_y); dev_free(w->sol_s);
+  w->c.destroy();
+  delete w;
+}
+
+// populate_on_failure / failure, scs.c:316-359
+static void populate_on_failure(int m, int n, ScsSolution *sol, ScsInfo *info, int status_val, const char *msg) {
+  if (info) {
+    info->gap = NAN; info->res_pri = NAN; info->res_dual = NAN; info->pobj = NAN; info->dobj = NAN;
+    info->iter = -1; info->status_val = status_val; info->solve_time = NAN;
+    strcpy(info->status, msg);
+    memset(&info->aa_stats, 0, sizeof(info->aa_stats));
+    info->aa_stats.last_aa_norm = NAN;
+  }
+  if (sol) {
+    if (n > 0) {
+      if (!sol->x) sol->x = (double *)calloc(n, sizeof(double));
+      for (int i = 0; i < n; ++i) sol->x[i] = NAN;
+    }
+    if (m > 0) {
+      if (!sol->y) sol->y = (double *)calloc(m, sizeof(double));
+      if (!sol->s) sol->s = (double *)calloc(m, sizeof(double));
+      for (int i = 0; i < m; ++i) { sol->y[i] = NAN; sol->s[i] = NAN; }
+    }
+  }
+}
+static int failure(SCS_WORK *w, int m, int n, ScsSolution *sol, ScsInfo *info, int stint, const char *msg,
+                   const char *ststr) {
+  (void)w;
+  populate_on_failure(m, n, sol, info, stint, ststr);
+  B200_PRINTF("Failure:%s\n", msg);
+  end_interrupt_listener();
+  return stint;
+}
+
+static void fill_aa_stats(SCS_WORK *w, ScsInfo *info) {
+  memset(&info->aa_stats, 0, sizeof(info->aa_stats));
+  info->aa_stats.last_aa_norm = NAN;
+  if (w->has_aa && w->aa.fetch_state() == 0) {
+    const AaState *h = w->aa.st_host;
+    AaStats &s = info->aa_stats;
+    s.iter = h->iter; s.n_accept = h->n_accept; s.n_reject_lapack = h->n_reject_lapack;
+    s.n_reject_rank0 = h->n_reject_rank0; s.n_reject_nonfinite = h->n_reject_nonfinite;
+    s.n_reject_weight_cap = h->n_reject_weight_cap; s.n_safeguard_reject = h->n_safeguard_reject;
+    s.last_rank = h->last_rank; s.last_aa_norm = h->last_aa_norm; s.last_regularization = h->last_regularization;
+  }
+}
+
+}  // namespace b200
+
+// ==================================================================== public API ======
+extern "C" const char *scs_version(void) { return B200_SCS_VERSION; }
+
+extern "C" void scs_set_default_settings(ScsSettings *stgs) {  // util.c:158-179
+  if (!stgs) return;
+  stgs->max_iters = 100000;
+  stgs->eps_abs = 1e-4;
+  stgs->eps_rel = 1e-4;
+  stgs->eps_infeas = 1e-7;
+  stgs->alpha = 1.5;
+  stgs->rho_x = 1e-6;
+  stgs->scale = 0.1;
+  stgs->verbose = 1;
+  stgs->normalize = 1;
+  stgs->warm_start = 0;
+  stgs->acceleration_lookback = 10;
+  stgs->acceleration_interval = 10;
+  stgs->acceleration_type_1 = 1;
+  stgs->acceleration_regularization = 1e-8;
+  stgs->acceleration_relaxation = 1.0;
+  stgs->adaptive_scale = 1;
+  stgs->write_data_filename = nullptr;
+  stgs->log_csv_filename = nullptr;
+  stgs->time_limit_secs = 0.;
+}
+
+extern "C" scs_int scs_update(ScsWork *w, scs_float *b, scs_float *c) {  // scs.c:1235-1273
+  if (!w) return -1;
+  const Clock::time_point t0 = Clock::now();
+  Ctx &cx = w->c;
+  if (cudaSetDevice(cx.device) != cudaSuccess) return -1;
+  const int n = w->n, m = w->m;
+  if (b) {
+    if (w->b_orig.data() != b) memcpy(w->b_orig.data(), b, sizeof(double) * m);
+    double nm = 0.0;
+    for (int i = 0; i < m; ++i) nm = fmax(nm, fabs(b[i]));
+    w->nm_b_orig = nm;
+  }
+  if (c) {
+    if (w->c_orig.data() != c) memcpy(w->c_orig.data(), c, sizeof(double) * n);
+    double nm = 0.0;
+    for (int i = 0; i < n; ++i) nm = fmax(nm, fabs(c[i]));
+    w->nm_c_orig = nm;
+  }
+  if (h2d(cx, w->b, w->b_orig.data(), (size_t)m) || h2d(cx, w->cvec, w->c_orig.data(), (size_t)n)) return -1;
+  if (w->stgs.normalize) {  // SCS(normalize_b_c), normalize.c:33-61
+    k_scale_bc<<<ew_grid(cx, n + m), kThreads, 0, cx.stream>>>(w->b, w->D, m, w->cvec, w->E, n, cx.red, cx.S);
+    k_scale_sigma<<<ew_grid(cx, n + m), kThreads, 0, cx.stream>>>(w->b, m, w->cvec, n, cx.S);
+    cx.launches += 2;
+    if (cx.fetch_scalars()) return -1;
+    w->primal_scale = w->dual_scale = cx.S_host->sigma;
+  } else {
+    if (cx.sync()) return -1;
+  }
+  w->setup_time = ms_since(t0);
+  return 0;
+}
+
+extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {  // scs.c:1193-1233
+  if (!d || !k || !stgs) {
+    B200_PRINTF("ERROR: Missing ScsData, ScsCone, or ScsSettings input\n");
+    return nullptr;
+  }
+  if (validate(d, k, stgs) < 0) {
+    B200_PRINTF("ERROR: Validation returned failure\n");
+    return nullptr;
+  }
+  const Clock::time_point t0 = Clock::now();
+  if (stgs->verbose) print_init_header(d, k, stgs);
+  SCS_WORK *w = new SCS_WORK();
+  w->n = d->n; w->m = d->m; w->l = d->n + d->m + 1;
+  const int n = w->n, m = w->m, l = w->l;
+  w->stgs = *stgs;
+  if (stgs->write_data_filename) w->write_fn = stgs->write_data_filename;
+  if (stgs->log_csv_filename) w->csv_fn = stgs->log_csv_filename;
+  w->stgs.write_data_filename = nullptr;  // rw.c is out of scope for this backend
+  w->stgs.log_csv_filename = nullptr;
+  bool ok = false;
+  do {
+    if (w->c.init(current_device())) break;
+    Ctx &c = w->c;
+    cudaStream_t st = c.stream;
+    if (w->ev.init()) break;
+    if (dev_alloc_zero(&w->u, (size_t)l, st) || dev_alloc_zero(&w->u_t, (size_t)l, st) ||
+        dev_alloc_zero(&w->v, (size_t)l, st) || dev_alloc_zero(&w->v_prev, (size_t)l, st) ||
+        dev_alloc_zero(&w->rsk, (size_t)l, st) || dev_alloc_zero(&w->g, (size_t)l, st) ||
+        dev_alloc_zero(&w->diag_r, (size_t)l, st) || dev_alloc_zero(&w->b, (size_t)m, st) ||
+        dev_alloc_zero(&w->cvec, (size_t)n, st) || dev_alloc(&w->D, (size_t)m) || dev_alloc(&w->E, (size_t)n) ||
+        dev_alloc_zero(&w->ws, (size_t)n, st) || dev_alloc_zero(&w->sol_x, (size_t)n, st) ||
+        dev_alloc_zero(&w->sol_y, (size_t)m, st) || dev_alloc_zero(&w->sol_s, (size_t)m, st)) {
+      B200_PRINTF("ERROR: work memory allocation failure\n");
+      break;
+    }
+    w->b_orig.assign((size_t)m, 0.0);
+    w->c_orig.assign((size_t)n, 0.0);
+    if (w->cone.init(&w->c, k, m)) { B200_PRINTF("ERROR: init_cone failure\n"); break; }
+    if (set_diag_r(w)) break;
+    if (w->ls.init(&w->c, d->A, d->P)) { B200_PRINTF("ERROR: init_lin_sys_work failure\n"); break; }
+    w->ls.diag_r = w->diag_r;
+    w->ls.own_diag_r = false;
+    k_fill<<<ew_grid(c, m), kThreads, 0, st>>>(w->D, 1.0, m);
+    k_fill<<<ew_grid(c, n), kThreads, 0, st>>>(w->E, 1.0, n);
+    c.launches += 2;
+    if (w->stgs.normalize) {
+      if (normalize_a_p_dev(w)) { B200_PRINTF("ERROR: normalize_a_p failure\n"); break; }
+    }
+    {  // one-time box normalisation by D (cones.c:1549-1557)
+      std::vector<double> Dh;
+      if (w->cone.bsize > 1 && w->stgs.normalize) {
+        Dh.resize((size_t)m);
+        if (d2h(c, Dh.data(), w->D, (size_t)m) || c.sync()) break;
+      }
+      if (w->cone.normalize_box(Dh.empty() ? nullptr : Dh.data())) break;
+    }
+    if (scs_update(w, d->b, d->c)) break;
+    if (w->ls.update_precond()) break;
+    if (w->stgs.acceleration_lookback) {
+      if (w->aa.init(&w->c, l, w->stgs.acceleration_lookback, w->stgs.acceleration_lookback,
+                     w->stgs.acceleration_type_1, w->stgs.acceleration_regularization,
+                     w->stgs.acceleration_relaxation, kAaSafeguard, kAaMaxWeight, kAaIrSteps) == 0) {
+        w->has_aa = w->aa.mem > 0;
+      } else {
+        // the reference continues without acceleration when aa_init fails (scs.c:1056-1058)
+        if (w->stgs.verbose) B200_PRINTF("WARN: aa_init returned NULL, no acceleration applied.\n");
+        w->aa.destroy();
+        w->has_aa = false;
+      }
+    }
+    if (c.sync()) break;
+    if (cudaGetLastError() != cudaSuccess) break;
+    ok = true;
+  } while (0);
+  if (!ok) {
+    free_work(w);
+    return nullptr;
+  }
+  w->setup_time = ms_since(t0);
+  return w;
+}
+
+extern "C" void scs_finish(ScsWork *w) { free_work(w); }
+
+extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_start) {  // scs.c:1275-1430
+  if (!sol || !w || !info) {
+    B200_PRINTF("ERROR: missing ScsWork, ScsSolution or ScsInfo input\n");
+    return SCS_FAILED;
+  }
+  Ctx &c = w->c;
+  if (cudaSetDevice(c.device) != cudaSuccess) return SCS_FAILED;
+  cudaStream_t st = c.stream;
+  const int n = w->n, m = w->m, l = w->l;
+  ScsSettings *stgs = &w->stgs;
+  stgs->warm_start = warm_start;
+  start_interrupt_listener();
+  const Clock::time_point t0 = Clock::now();
+  strcpy(info->lin_sys_solver, scs_get_lin_sys_method());
+  info->status_val = SCS_UNFINISHED;
+  // ---- update_work: reset_tracking + warm/cold start + g (scs.c:1079-1105)
+  w->last_scale_update_iter = 0; w->sum_log_scale_factor = 0.; w->n_log_scale_factor = 0; w->scale_updates = 0;
+  w->time_limit_reached = 0;
+  w->r_n.last_iter = -1; w->r_o.last_iter = -1;
+  w->ev.reset();
+  cudaMemsetAsync(&c.S->aa_rejected, 0, 2 * sizeof(int), st);  // safeguard counters of this solve
+  if (warm_start) {
+    if (!sol->x || !sol->y || !sol->s) {
+      return failure(w, m, n, sol, info, SCS_FAILED, "warm-start requested without x, y, s", "failure");
+    }
+    if (h2d(c, w->sol_x, sol->x, (size_t)n) || h2d(c, w->sol_y, sol->y, (size_t)m) || h2d(c, w->sol_s, sol->s, (size_t)m))
+      return failure(w, m, n, sol, info, SCS_FAILED, "warm-start upload", "failure");
+    k_warm_start<<<ew_grid(c, l), kThreads, 0, st>>>(w->v, w->sol_x, w->sol_y, w->sol_s, w->D, w->E, w->diag_r, n, m,
+                                                     w->primal_scale, w->dual_scale);
+  } else {
+    k_cold_start<<<ew_grid(c, l), kThreads, 0, st>>>(w->v, l);
+  }
+  c.launches++;
+  if (update_work_cache(w)) return failure(w, m, n, sol, info, SCS_FAILED, "error in update_work_cache", "failure");
+  if (stgs->verbose) print_header();
+
+  const int gl = ew_grid(c, l);
+  const int zl = w->cone.z + w->cone.l;
+  const bool accel = w->has_aa;
+  const int interval = stgs->acceleration_interval;
+  const double bytes_iter_fixed = 14.0 * l * 8.0;
+  int i;
+  for (i = 0; i < stgs->max_iters; ++i) {
+    // ---- Anderson acceleration (scs.c:1306-1313)
+    if (accel && i > 0 && i % interval == 0) {
+      const int sl = w->ev.begin(2, st);
+      if (w->aa.apply(w->v, w->v_prev, &c.S->vnorm2))
+        return failure(w, m, n, sol, info, SCS_FAILED, "error in aa_apply", "failure");
+      w->ev.end(sl, st);
+      w->alg_bytes += (3.0 * w->aa.mem + 12.0) * l * 8.0;
+    }
+    // ---- linear system (scs.c:1326-1332)
+    const int sl_lin = w->ev.begin(0, st);
+    if (accel)
+      k_prep<true><<<gl, kThreads, 0, st>>>(w->v, w->v_prev, w->u_t, w->u, w->g, w->diag_r, w->ws, n, m, i, c.red, c.S);
+    else
+      k_prep<false><<<gl, kThreads, 0, st>>>(w->v, w->v_prev, w->u_t, w->u, w->g, w->diag_r, w->ws, n, m, i, c.red, c.S);
+    c.launches++;
+    if (w->ls.solve_dev(w->u_t, w->ws, 0))
+      return failure(w, m, n, sol, info, SCS_FAILED, "error in project_lin_sys", "failure");
+    k_rootplus<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->u_t, w->v, w->g, w->diag_r, n + m, i, c.red, c.S);
+    c.launches++;
+    w->ev.end(sl_lin, st);
+    {
+      const int K = w->ls.last_its;
+      w->alg_bytes += (K + 2.0) * (w->ls.bytes_A() + w->ls.bytes_At()) + (K + 1.0) * w->ls.bytes_P() +
+                      K * 10.0 * n * 8.0 + 6.0 * (n + m) * 8.0 + bytes_iter_fixed;
+    }
+    // ---- cones (scs.c:1334-1340)
+    const int sl_cone = w->ev.begin(1, st);
+    k_pre<<<gl, kThreads, 0, st>>>(w->u_t, w->u, w->rsk, w->v, w->g, w->diag_r, n, m, w->cone.z, zl, i, c.S);
+    c.launches++;
+    if (w->cone.has_nonlinear()) {
+      if (w->cone.project_nonlinear(w->u + n, w->rsk + n, w->diag_r + n))
+        return failure(w, m, n, sol, info, SCS_FAILED, "error in project_cones", "failure");
+    }
+    w->ev.end(sl_cone, st);
+
+    const bool check = (i % kConvergedInterval == 0);
+    const bool print = stgs->verbose && (i % kPrintInterval == 0);
+    if (check || print) {
+      k_post<1><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, l, stgs->alpha, c.red, c.S);
+      c.launches++;
+      if (check && g_int_detected) return failure(w, m, n, sol, info, SCS_SIGINT, "interrupted", "interrupted");
+      if (populate_residuals(w, i)) return failure(w, m, n, sol, info, SCS_FAILED, "error in residuals", "failure");
+      w->alg_bytes += w->ls.bytes_A() + w->ls.bytes_At() + w->ls.bytes_P() + 20.0 * l * 8.0;
+      if (check) {
+        if ((info->status_val = has_converged(w)) != 0) break;
+        if (stgs->time_limit_secs && ms_since(t0) > 1000. * stgs->time_limit_secs) {
+          w->time_limit_reached = 1;
+          break;
+        }
+      }
+      if (print) print_summary(w, i, t0);
+      if (stgs->adaptive_scale && i == w->r_o.last_iter) {
+        if (update_scale(w, i) < 0) return failure(w, m, n, sol, info, SCS_FAILED, "error in update_scale", "failure");
+      }
+      k_post<2><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, l, stgs->alpha, c.red, c.S);
+      c.launches++;
+    } else {
+      k_post<0><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, l, stgs->alpha, c.red, c.S);
+      c.launches++;
+    }
+    // ---- AA safeguard (scs.c:1386-1394); the aa_norm > 0 gate is evaluated on the device
+    if (accel && i > 0 && i % interval == 0) {
+      const int sl = w->ev.begin(2, st);
+      if (w->aa.safeguard(w->v, w->v_prev, &c.S->vnorm2, &c.S->aa_rejected, &c.S->aa_accepted))
+        return failure(w, m, n, sol, info, SCS_FAILED, "error in aa_safeguard", "failure");
+      w->ev.end(sl, st);
+    }
+    if (w->ev.used > EventAccum::kSlots - 8) {
+      if (c.sync()) return failure(w, m, n, sol, info, SCS_FAILED, "sync", "failure");
+      w->ev.flush();
+    }
+  }
+  w->admm_iters += i;
+  if (stgs->verbose) {
+    if (populate_residuals(w, i)) return failure(w, m, n, sol, info, SCS_FAILED, "error in residuals", "failure");
+    print_summary(w, i, t0);
+  }
+  // ---- finalize (scs.c:874-924)
+  if (!sol->x) sol->x = (double *)calloc(n, sizeof(double));
+  if (!sol->y) sol->y = (double *)calloc(m, sizeof(double));
+  if (!sol->s) sol->s = (double *)calloc(m, sizeof(double));
+  k_finalize_sol<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->sol_x, w->sol_y, w->sol_s, w->u, w->rsk, w->D, w->E, n, m,
+                                                         w->primal_scale, w->dual_scale, c.red, c.S);
+  c.launches++;
+  if (populate_residuals(w, i)) return failure(w, m, n, sol, info, SCS_FAILED, "error in residuals", "failure");
+  if (c.fetch_scalars()) return failure(w, m, n, sol, info, SCS_FAILED, "fetch", "failure");
+  w->ev.flush();
+  const double nm_s = c.S_host->fin[0], nm_y = c.S_host->fin[1], sty = c.S_host->fin[2];
+  const HostResid &r = w->r_o;
+  info->setup_time = w->setup_time;
+  info->iter = i;
+  info->res_infeas = r.res_infeas;
+  info->res_unbdd_a = r.res_unbdd_a;
+  info->res_unbdd_p = r.res_unbdd_p;
+  info->scale = stgs->scale;
+  info->scale_updates = w->scale_updates;
+  info->rejected_accel_steps = c.S_host->aa_rejected;
+  info->accepted_accel_steps = c.S_host->aa_accepted;
+  fill_aa_stats(w, info);
+  info->comp_slack = fabs(sty);
+  if (info->comp_slack > 1e-5 * fmax(nm_s, nm_y))
+    B200_PRINTF("WARNING - large complementary slackness residual: %f\n", info->comp_slack);
+  double fx = 1.0, fy = 1.0, fs = 1.0;
+  auto set_solved = [&]() {  // scs.c:805-816
+    fx = fy = fs = safediv_pos_h(1.0, r.tau);
+    info->gap = r.gap; info->res_pri = r.res_pri; info->res_dual = r.res_dual;
+    info->pobj = r.xt_p_x / 2. + r.ctx;
+    info->dobj = -r.xt_p_x / 2. - r.bty;
+    strcpy(info->status, "solved");
+    info->status_val = SCS_SOLVED;
+  };
+  auto set_infeasible = [&]() {  // scs.c:818-829
+    fy = -1 / r.bty_tau; fx = NAN; fs = NAN;
+    info->gap = NAN; info->res_pri = NAN; info->res_dual = NAN; info->pobj = INFINITY; info->dobj = INFINITY;
+    strcpy(info->status, "infeasible");
+    info->status_val = SCS_INFEASIBLE;
+  };
+  auto set_unbounded = [&]() {  // scs.c:831-842
+    fx = -1 / r.ctx_tau; fs = -1 / r.ctx_tau; fy = NAN;
+    info->gap = NAN; info->res_pri = NAN; info->res_dual = NAN; info->pobj = -INFINITY; info->dobj = -INFINITY;
+    strcpy(info->status, "unbounded");
+    info->status_val = SCS_UNBOUNDED;
+  };
+  switch (info->status_val) {
+    case SCS_SOLVED: set_solved(); break;
+    case SCS_INFEASIBLE: set_infeasible(); break;
+    case SCS_UNBOUNDED: set_unbounded(); break;
+    case SCS_UNFINISHED:  // set_unfinished, scs.c:845-871
+      if (r.kap > r.tau && (r.bty_tau < 0 || r.ctx_tau < 0)) {
+        if (r.bty_tau < 0 && r.bty_tau < r.ctx_tau) { set_infeasible(); info->status_val = SCS_INFEASIBLE_INACCURATE; }
+        else { set_unbounded(); info->status_val = SCS_UNBOUNDED_INACCURATE; }
+      } else if (r.tau > 0) {
+        set_solved();
+        info->status_val = SCS_SOLVED_INACCURATE;
+      } else {
+        B200_PRINTF("ERROR: could not determine problem status.\n");
+        strcpy(info->status, "failure");
+        info->status_val = SCS_FAILED;
+      }
+      if (w->time_limit_reached) strcat(info->status, " (inaccurate - reached time_limit_secs)");
+      else if (info->iter >= stgs->max_iters) strcat(info->status, " (inaccurate - reached max_iters)");
+      else B200_PRINTF("ERROR: should not be in this state (1).\n");
+      break;
+    default: B200_PRINTF("ERROR: should not be in this state (2).\n");
+  }
+  k_scale3<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->sol_x, n, fx, w->sol_y, w->sol_s, m, fy, fs);
+  c.launches++;
+  if (d2h(c, sol->x, w->sol_x, (size_t)n) || d2h(c, sol->y, w->sol_y, (size_t)m) || d2h(c, sol->s, w->sol_s, (size_t)m) ||
+      c.sync())
+    return failure(w, m, n, sol, info, SCS_FAILED, "solution download", "failure");
+  w->ev.flush();
+  info->solve_time = ms_since(t0);
+  info->lin_sys_time = w->ev.total[0];
+  info->cone_time = w->ev.total[1];
+  info->accel_time = w->ev.total[2];
+  if (stgs->verbose) print_footer(info);
+  end_interrupt_listener();
+  return info->status_val;
+}
+
+extern "C" scs_int scs(const ScsData *d, const ScsCone *k, const ScsSettings *stgs, ScsSolution *sol,
+                       ScsInfo *info) {  // scs.c:1483-1496
+  scs_int status;
+  ScsWork *w = scs_init(d, k, stgs);
+  if (w) {
+    scs_solve(w, sol, info, stgs->warm_start);
+    status = info->status_val;
+  } else {
+    status = failure(nullptr, d ? d->m : -1, d ? d->n : -1, sol, info, SCS_FAILED, "could not initialize work",
+                     "failure");
+  }
+  scs_finish(w);
+  return status;
+}
+
+// ------------------------------------------------------------------ measurement -------
+extern "C" scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out) {
+  if (!w || !out) return -1;
+  out->kernel_launches = w->c.launches;
+  out->cg_iters = w->ls.tot_cg_its;
+  out->admm_iters = w->admm_iters;
+  out->spmv_calls = w->c.spmv_calls;
+  out->spmv_ms = 0.0;
+  out->algorithmic_bytes = w->alg_bytes;
+  out->h2d_bytes = w->c.h2d;
+  out->d2h_bytes = w->c.d2h;
+  return 0;
+}
+
+extern "C" double scs_b200_bench_spmv(ScsWork *w, scs_int which, scs_int reps, double *alg_bytes) {
+  if (!w || reps <= 0) return -1.0;
+  Ctx &c = w->c;
+  if (cudaSetDevice(c.device) != cudaSuccess) return -1.0;
+  LinSys &ls = w->ls;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1.0;
+  // operate on CG scratch only: p (n) -> tmp (m) -> Gp (n); ADMM state is untouched
+  k_fill<<<ew_grid(c, ls.n), kThreads, 0, c.stream>>>(ls.p, 1.0, ls.n);
+  k_fill<<<ew_grid(c, ls.m), kThreads, 0, c.stream>>>(ls.tmp, 1.0, ls.m);
+  for (int wu = 0; wu < 2; ++wu) {
+    if (which == 0) ls.launch_A_scaled(ls.p, ls.tmp, nullptr);
+    else ls.launch_G(ls.tmp, ls.p, ls.Gp, nullptr);
+  }
+  cudaEventRecord(e0, c.stream);
+  for (int r = 0; r < reps; ++r) {
+    if (which == 0) ls.launch_A_scaled(ls.p, ls.tmp, nullptr);
+    else ls.launch_G(ls.tmp, ls.p, ls.Gp, nullptr);
+  }
+  cudaEventRecord(e1, c.stream);
+  if (cudaStreamSynchronize(c.stream) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (alg_bytes) *alg_bytes = which == 0 ? ls.bytes_A() : (ls.bytes_At() + ls.bytes_P());
+  return (double)ms / reps;
+}
+
+extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, const ScsCone *const *k,
+                                        const ScsSettings *stgs, ScsSolution *const *sol, ScsInfo *info,
+                                        scs_int streams) {
+  (void)streams;
+  if (count < 0 || !d || !k || !stgs || !sol || !info) return -1;
+  scs_int worst = 0;
+  for (scs_int i = 0; i < count; ++i) {
+    const scs_int st = scs(d[i], k[i], stgs, sol[i], &info[i]);
+    if (st < 0 && st != SCS_INFEASIBLE && st != SCS_UNBOUNDED) worst = st;
+  }
+  return worst;
+}
