@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- ADMM iterations/sec of the SCS hot path on the BASELINE.json headline workload.
+
+    python bench.py --gpus N --steps K --warmup W            # B200 backend (this repo)
+    python bench.py --impl reference --steps K --warmup W    # reference CPU_INDIRECT on host cores
+
+Workload (BASELINE.json configs[1]): sparse LASSO in the reference's
+documentation formulation with data matrix Ad in R^{2M x 1M}, 100 nnz per column =>
+SCS n = 4M, m = 4M, nnz(A) = 106M, nnz(P) = 2M, cone {z: 2M, l: 2M}.  Synthetic, seeded.
+
+A "step" is `--iters-per-step` (default 25 = CONVERGED_INTERVAL) ADMM iterations.
+
+  value : device-resident throughput.  One scs_solve call per rank runs (W+K) steps with the
+          stopping tolerances at 0; the K timed steps are iterations [W*ips, (W+K)*ips) of that
+          call, timed with CUDA events on the solve stream (inputs resident in HBM).  A barrier +
+          device synchronize bracket the call on both sides; the MAX over ranks is used.
+  e2e   : the same metric through the public API with HOST buffers: every step is
+          scs_update(b, c) [H2D] + scs_solve(max_iters=ips, cold start) [x, y, s D2H], wall clock.
+  N > 1 : every rank solves its own LASSO instance (seed + rank) on its own GPU, no data-path
+          collective ("weak" scaling); torch.distributed (NCCL) is only the barrier / max plumbing.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FULL = dict(n0=1_000_000, m0=2_000_000, nnz_per_col=100)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--iters-per-step", type=int, default=25)
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full workload (dev runs only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-time-to-eps", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0)
+    return ap.parse_args()
+
+
+def workload(scale, seed):
+    from scs_python_b200 import problems
+    n0 = max(1000, int(FULL["n0"] * scale))
+    m0 = 2 * n0
+    data, cone, aux = problems.lasso(n0, m0, FULL["nnz_per_col"], seed)
+    desc = dict(workload="sparse LASSO QP (reference doc formulation), Ad %dx%d, %d nnz/col" % (m0, n0, FULL["nnz_per_col"]),
+                n=int(data["A"].shape[1]), m=int(data["A"].shape[0]), nnz_A=int(data["A"].nnz),
+                nnz_P=int(data["P"].nnz), cone="z=%d,l=%d" % (cone["z"], cone["l"]), scale=scale,
+                l2_policy="inputs_exceed_l2 (A+A' = %.2f GB >> 126 MB L2)" % (2 * 12e-9 * data["A"].nnz))
+    return data, cone, desc
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("spmv_g_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    td = None
+    if world > 1:
+        import torch
+        import torch.distributed as td_
+        torch.cuda.set_device(local)
+        td_.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        td = td_
+    return rank, world, local, td
+
+
+def barrier_sync(td, local):
+    import torch
+    if td is not None:
+        td.barrier()
+    torch.cuda.synchronize(local)
+
+
+def _dev(local):
+    import torch
+    return local if isinstance(local, torch.device) else torch.device("cuda", local)
+
+
+def max_over_ranks(td, local, x):
+    if td is None:
+        return float(x)
+    import torch
+    t = torch.tensor([float(x)], dtype=torch.float64, device=_dev(local))
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(td, local, x):
+    if td is None:
+        return float(x)
+    import torch
+    t = torch.tensor([float(x)], dtype=torch.float64, device=_dev(local))
+    td.all_reduce(t, op=td.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------ reference --
+def import_reference():
+    """Reference python package from oracle/_ref (OpenMP build first).  Returns (module, kind)."""
+    for sub in ("scs_omp", ""):
+        p = os.path.join(ROOT, "oracle", "_ref", sub) if sub else os.path.join(ROOT, "oracle", "_ref")
+        if os.path.exists(os.path.join(p, "scs", "__init__.py")):
+            sys.path.insert(0, p)
+            try:
+                import scs  # noqa
+                return scs, ("reference (oracle/_ref/%s, CPU_INDIRECT%s)" % (sub or "scs", ", OpenMP" if sub else ""))
+            except Exception:
+                sys.path.pop(0)
+                for k in [k for k in sys.modules if k == "scs" or k.startswith("scs.")]:
+                    del sys.modules[k]
+    return None, None
+
+
+def reference_steps(data, cone, ips, steps, warmup, budget_s):
+    """Times the reference CPU_INDIRECT path: every step = update(b, c) + solve(max_iters=k, cold)."""
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cores))
+    scs, kind = import_reference()
+    t0 = time.perf_counter()
+    if scs is not None:
+        mk = lambda k: scs.SCS(data, cone, linear_solver=scs.LinearSolver.CPU_INDIRECT, verbose=False, max_iters=k,
+                               eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0)
+        port = False
+    else:  # no compiled reference on this box: the numpy restatement ("port")
+        from oracle import scs_oracle as O
+        kind = "port (oracle/scs_oracle.py, numpy)"
+        cores = 1
+
+        class _W:
+            def __init__(self, k):
+                self.s = O.ScsOracle(data, cone, max_iters=k, eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0)
+
+            def update(self, b, c):
+                self.s.update(b, c)
+
+            def solve(self, warm_start=False):
+                return self.s.solve(warm_start)
+        mk = lambda k: _W(k)
+        port = True
+    k = ips
+    solver = mk(k)
+    setup_s = time.perf_counter() - t0
+    total_steps = steps + warmup
+    times, iters = [], []
+    for s in range(total_steps):
+        t = time.perf_counter()
+        solver.update(data["b"], data["c"])
+        sol = solver.solve(warm_start=False)
+        dt = time.perf_counter() - t
+        it = int(sol["info"]["iter"])
+        if s >= warmup:
+            times.append(dt); iters.append(it)
+        # keep the whole run inside the budget: shrink the per-step sample if needed
+        remaining = total_steps - (s + 1)
+        if remaining > 0 and dt * remaining > max(1.0, budget_s - (time.perf_counter() - t0)) and k > 1:
+            k_new = max(1, int(k * max(0.05, (budget_s - (time.perf_counter() - t0)) / (dt * remaining))))
+            if k_new < k:
+                k = k_new
+                solver = mk(k)
+                if s + 1 <= warmup:
+                    pass
+    tot_t, tot_i = float(np.sum(times)), int(np.sum(iters))
+    return dict(value=tot_i / tot_t if tot_t > 0 else 0.0, kind=kind, cores=cores, setup_s=setup_s,
+                ms_per_step=1e3 * tot_t / max(1, len(times)), iters_per_step=(tot_i / max(1, len(times))),
+                port=port)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    data, cone, desc = workload(args.scale, seed=0)
+    r = reference_steps(data, cone, args.iters_per_step, args.steps, args.warmup, args.ref_budget_s)
+    sample = ("full workload, %s, each step = scs.update(b,c) + scs.solve(max_iters=%.1f, cold start) incl. the "
+              "per-call g = (R+M)^-1 h solve; setup %.1f s not timed" % (r["kind"], r["iters_per_step"], r["setup_s"]))
+    line = dict(impl="reference", metric="admm_iters_per_sec", value=r["value"], unit="iters/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=r["ms_per_step"], higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=desc,
+                cpu_baseline=dict(value=r["value"], unit="iters/s", cores=r["cores"],
+                                  kind="port" if r["port"] else "reference", sample=sample),
+                e2e=dict(value=r["value"], unit="iters/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline_sample(ips):
+    """Reference CPU path on a bounded 1/16-scale sample of the same workload (rank 0, N=1)."""
+    scale = 1.0 / 16.0
+    data, cone, desc = workload(scale, seed=0)
+    r = reference_steps(data, cone, ips, steps=2, warmup=1, budget_s=45.0)
+    return dict(value=r["value"], unit="iters/s", cores=r["cores"], kind="port" if r["port"] else "reference",
+                sample="%s on a 1/16-scale instance of the workload (n=%d, m=%d, nnz(A)=%d): 2 steps of "
+                       "update+solve(max_iters=%.0f) after 1 warm-up; per-iteration cost is linear in nnz, so the "
+                       "full-size rate is ~1/16 of this" % (r["kind"], desc["n"], desc["m"], desc["nnz_A"], r["iters_per_step"]),
+                value_scaled_to_full_workload=r["value"] * scale)
+
+
+# ------------------------------------------------------------------------------------ ours --
+def run_b200(args):
+    rank, world, local, td = dist_setup(args.gpus)
+    import scs_python_b200 as scsb
+    from scs_python_b200 import _scs_b200 as B
+    if B.lib.scs_b200_device_count() <= 0:
+        raise RuntimeError("bench.py: no CUDA device visible; the B200 backend has no CPU fallback")
+    if B.lib.scs_b200_set_device(local) != 0:
+        raise RuntimeError("bench.py: cannot select CUDA device %d" % local)
+    import torch
+    torch.cuda.set_device(local)
+    ips, K, W = args.iters_per_step, args.steps, args.warmup
+    data, cone, desc = workload(args.scale, seed=rank)
+    n, m = desc["n"], desc["m"]
+
+    t_setup = time.perf_counter()
+    solver = scsb.SCS(data, cone, verbose=False, eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0, max_iters=(W + K) * ips)
+    setup_s = time.perf_counter() - t_setup
+    inner = solver._solver
+
+    # ---- device-resident timed region
+    inner.set_marks(W * ips, (W + K) * ips)
+    sampler = ClockSampler(local)
+    barrier_sync(td, local)
+    sampler.start()
+    sol = solver.solve(warm_start=False)
+    barrier_sync(td, local)
+    clocks = sampler.stop()
+    mk = inner.get_marks()
+    assert mk is not None and mk["iters"] == K * ips, "timed region did not cover exactly K steps: %s" % (mk,)
+    ms_max = max_over_ranks(td, local, mk["ms"])
+    total_iters = sum_over_ranks(td, local, mk["iters"])
+    value = total_iters / (ms_max * 1e-3)
+    launches = int(sum_over_ranks(td, local, mk["kernel_launches"]))
+
+    # ---- end-to-end through the public API with host buffers
+    e2e_t, e2e_i = 0.0, 0
+    e2e_solver = scsb.SCS(data, cone, verbose=False, eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0, max_iters=ips)
+    st0 = e2e_solver._solver.stats()
+    for s in range(W + K):
+        if s == W:
+            st0 = e2e_solver._solver.stats()
+            barrier_sync(td, local)
+        t = time.perf_counter()
+        e2e_solver.update(data["b"], data["c"])
+        so = e2e_solver.solve(warm_start=False)
+        dt = time.perf_counter() - t
+        if s >= W:
+            e2e_t += dt; e2e_i += int(so["info"]["iter"])
+    barrier_sync(td, local)
+    st1 = e2e_solver._solver.stats()
+    e2e_t_max = max_over_ranks(td, local, e2e_t)
+    e2e_value = sum_over_ranks(td, local, e2e_i) / e2e_t_max
+    h2d_step = (st1["h2d_bytes"] - st0["h2d_bytes"]) / max(1, K)
+    d2h_step = (st1["d2h_bytes"] - st0["d2h_bytes"]) / max(1, K)
+    e2e_solver._solver.finish()
+
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        g_ms = mk["spmv_g_ms"] / max(1, mk["spmv_g_launches"])
+        a_ms = mk["spmv_a_ms"] / max(1, mk["spmv_a_launches"])
+        ach = mk["bytes_g"] / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
+        roofline = dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=ncu_traffic(),
+                        kernel="row_kernel<ElemMul,ElemMul,EpiG,DUAL> (Gp = A' z + P p + R_x p, p'Gp fused)",
+                        avg_launch_ms=g_ms, launches_timed=int(mk["spmv_g_launches"]),
+                        algorithmic_bytes_per_launch=mk["bytes_g"], peak_source=peak_src,
+                        second_kernel=dict(kernel="row_kernel<ElemMul,ElemMul,EpiScaleRy> (z = R_y^-1 A p)",
+                                           avg_launch_ms=a_ms, launches_timed=int(mk["spmv_a_launches"]),
+                                           achieved=(mk["bytes_a"] / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0)),
+                        iteration_model=dict(algorithmic_bytes=mk["algorithmic_bytes"],
+                                             achieved=mk["algorithmic_bytes"] / (mk["ms"] * 1e-3) / 1e9,
+                                             frac=mk["algorithmic_bytes"] / (mk["ms"] * 1e-3) / 1e9 / peak,
+                                             spmv_share_of_step=(mk["spmv_g_ms"] + mk["spmv_a_ms"]) / mk["ms"]))
+        out = dict(metric="admm_iters_per_sec", value=value, unit="iters/s", n_gpus=world, steps=K, warmup=W,
+                   ms_per_step=ms_max / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                   data="synthetic", config=dict(desc, iters_per_step=ips, parallelism="independent instance per GPU"),
+                   clocks=clocks,
+                   e2e=dict(value=e2e_value, unit="iters/s", h2d_bytes_per_step=h2d_step, d2h_bytes_per_step=d2h_step,
+                            note="step = scs_update(b,c) + scs_solve(max_iters=%d, cold start) incl. the per-call "
+                                 "g solve; host numpy buffers in, x/y/s out" % ips),
+                   gpu_launches=launches, roofline=roofline,
+                   cg_iters_per_admm_iter=mk["cg_iters"] / max(1, mk["iters"]), setup_s=setup_s)
+    solver._solver.finish()
+
+    # ---- time to eps = 1e-4 (the second half of BASELINE.json's metric), rank 0 only
+    if rank == 0 and not args.no_time_to_eps:
+        t = time.perf_counter()
+        s2 = scsb.SCS(data, cone, verbose=False, max_iters=5000)
+        r2 = s2.solve(warm_start=False)
+        wall = time.perf_counter() - t
+        i2 = r2["info"]
+        out["time_to_eps"] = dict(eps=1e-4, status=i2["status"], iters=i2["iter"], setup_ms=i2["setup_time"],
+                                  solve_ms=i2["solve_time"], wall_s_incl_upload=wall, pobj=i2["pobj"], dobj=i2["dobj"],
+                                  res_pri=i2["res_pri"], res_dual=i2["res_dual"], gap=i2["gap"])
+        s2._solver.finish()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_baseline_sample(ips)
+        except Exception as e:  # the checker must never take the product line down
+            out["cpu_baseline"] = dict(value=None, unit="iters/s", cores=0, kind="reference", sample="failed: %r" % (e,))
+    if td is not None:
+        td.barrier()
+        td.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

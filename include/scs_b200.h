@@ -242,6 +242,22 @@ scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out);
  * with CUDA events on that stream; *alg_bytes gets the algorithmic bytes of one launch. */
 double scs_b200_bench_spmv(ScsWork *w, scs_int which, scs_int reps, double *alg_bytes);
 
+/* Iteration marks: the next scs_solve records a CUDA event on the workspace stream at the
+ * top of ADMM iteration `begin_iter` and of `end_iter` (or at loop exit if earlier), and
+ * switches per-launch event timing of the SpMV kernels on between them. */
+scs_int scs_b200_set_marks(ScsWork *w, scs_int begin_iter, scs_int end_iter);
+typedef struct {
+  double ms;                 /* device time between the two marks (CUDA events) */
+  long long iters;           /* ADMM iterations between the marks */
+  long long cg_iters;        /* CG iterations between the marks */
+  long long kernel_launches; /* kernels of this library launched between the marks */
+  double algorithmic_bytes;  /* SURVEY.md 8(d) byte model between the marks */
+  double spmv_a_ms, spmv_g_ms;           /* summed device time of the two SpMV kernels */
+  long long spmv_a_launches, spmv_g_launches; /* real (not early-exit) launches timed */
+  double bytes_a, bytes_g;   /* algorithmic bytes of ONE launch of each kernel */
+} ScsB200Marks;
+scs_int scs_b200_get_marks(const ScsWork *w, ScsB200Marks *out);
+
 /* Solve `count` independent problems on the current device, one after another on
  * `streams` concurrent streams (batch sharding across GPUs is done by the caller: one
  * process per GPU, problem i -> rank i % world).  Arrays of pointers, one per problem. */

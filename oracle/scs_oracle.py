@@ -638,11 +638,12 @@ def proj_dual_cone(x, c: ConeWork, D, r_y):
     if not c.scaled_cones:
         if k["bsize"] and len(k["bu"]) and len(k["bl"]):
             c.box_t_warm_start = 1.0
-            Db = D[k["z"] + k["l"]:] if D is not None else None
-            for j in range(k["bsize"] - 1):  # normalize_box_cone, cones.c:1153-1169
-                factor = Db[j + 1] / Db[0] if Db is not None else 1.0
-                k["bu"][j] = math.inf if k["bu"][j] >= MAX_BOX_VAL else k["bu"][j] * factor
-                k["bl"][j] = -math.inf if k["bl"][j] <= -MAX_BOX_VAL else k["bl"][j] * factor
+            if D is not None:  # only with a scaling struct (cones.c:1553-1554)
+                Db = D[k["z"] + k["l"]:]
+                for j in range(k["bsize"] - 1):  # normalize_box_cone, cones.c:1153-1169
+                    factor = Db[j + 1] / Db[0]
+                    k["bu"][j] = math.inf if k["bu"][j] >= MAX_BOX_VAL else k["bu"][j] * factor
+                    k["bl"][j] = -math.inf if k["bl"][j] <= -MAX_BOX_VAL else k["bl"][j] * factor
         c.scaled_cones = True
     s = x.copy()
     if r_y is not None:

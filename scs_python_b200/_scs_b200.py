@@ -87,6 +87,13 @@ class ScsB200Stats(C.Structure):
                 ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong)]
 
 
+class ScsB200Marks(C.Structure):
+    _fields_ = [("ms", c_double), ("iters", C.c_longlong), ("cg_iters", C.c_longlong),
+                ("kernel_launches", C.c_longlong), ("algorithmic_bytes", c_double), ("spmv_a_ms", c_double),
+                ("spmv_g_ms", c_double), ("spmv_a_launches", C.c_longlong), ("spmv_g_launches", C.c_longlong),
+                ("bytes_a", c_double), ("bytes_g", c_double)]
+
+
 # --- prototypes (include/scs_b200.h) ---
 lib.scs_init.restype = C.c_void_p
 lib.scs_init.argtypes = [C.POINTER(ScsData), C.POINTER(ScsCone), C.POINTER(ScsSettings)]
@@ -136,6 +143,10 @@ lib.scs_b200_set_device.argtypes = [c_int]
 lib.scs_b200_device_count.restype = c_int
 lib.scs_b200_get_stats.restype = c_int
 lib.scs_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(ScsB200Stats)]
+lib.scs_b200_set_marks.restype = c_int
+lib.scs_b200_set_marks.argtypes = [C.c_void_p, c_int, c_int]
+lib.scs_b200_get_marks.restype = c_int
+lib.scs_b200_get_marks.argtypes = [C.c_void_p, C.POINTER(ScsB200Marks)]
 lib.scs_b200_bench_spmv.restype = c_double
 lib.scs_b200_bench_spmv.argtypes = [C.c_void_p, c_int, c_int, p_double]
 
@@ -424,6 +435,18 @@ class SCS(object):
                 raise ValueError("Workspace not initialized!")
             lib.scs_b200_get_stats(self._work, C.byref(st))
         return {f: getattr(st, f) for f, _ in ScsB200Stats._fields_}
+
+    def set_marks(self, begin_iter, end_iter):
+        with self._lock:
+            if lib.scs_b200_set_marks(self._work, int(begin_iter), int(end_iter)) != 0:
+                raise ValueError("invalid iteration marks")
+
+    def get_marks(self):
+        mk = ScsB200Marks()
+        with self._lock:
+            if lib.scs_b200_get_marks(self._work, C.byref(mk)) != 0:
+                return None
+        return {f: getattr(mk, f) for f, _ in ScsB200Marks._fields_}
 
     def bench_spmv(self, which, reps):
         ab = c_double(0.0)

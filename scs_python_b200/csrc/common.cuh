@@ -92,6 +92,19 @@ enum ResIdx {
   R_COUNT
 };
 
+// Optional per-launch CUDA-event timing of the SpMV kernels (bench.py roofline): events are
+// recorded on the launching stream inside the timed region; launches enqueued after CG had
+// already converged (no-op early exits) are recognised by their tag and left out.
+struct KernelProf {
+  static constexpr int kN = 1024;
+  bool on = false, created = false;
+  cudaEvent_t a[kN], b[kN];
+  int cat[kN], tag[kN];
+  int used = 0;
+  double ms[4] = {0, 0, 0, 0};
+  long long cnt[4] = {0, 0, 0, 0};
+};
+
 struct Ctx {
   int device = 0;
   int sms = 148;
@@ -103,7 +116,44 @@ struct Ctx {
   cudaEvent_t ev = nullptr;
   // counters
   long long launches = 0, spmv_calls = 0, h2d = 0, d2h = 0;
+  KernelProf prof;
   int grid_ew() const { return sms * kCtasPerSm; }
+
+  int prof_enable(bool on) {
+    if (on && !prof.created) {
+      for (int i = 0; i < KernelProf::kN; ++i) {
+        CUDA_OK(cudaEventCreate(&prof.a[i]));
+        CUDA_OK(cudaEventCreate(&prof.b[i]));
+      }
+      prof.created = true;
+    }
+    prof.on = on;
+    return 0;
+  }
+  // tag: CG iteration index of the launch inside the current solve, or -1 (always real)
+  int prof_begin(int category, int tag) {
+    if (!prof.on || prof.used >= KernelProf::kN) return -1;
+    const int s = prof.used++;
+    prof.cat[s] = category;
+    prof.tag[s] = tag;
+    cudaEventRecord(prof.a[s], stream);
+    return s;
+  }
+  void prof_end(int slot) {
+    if (slot >= 0) cudaEventRecord(prof.b[slot], stream);
+  }
+  // call right after a stream synchronisation; real_its = CG iterations actually executed
+  void prof_flush(int real_its) {
+    for (int i = 0; i < prof.used; ++i) {
+      if (prof.tag[i] >= 0 && prof.tag[i] >= real_its) continue;
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, prof.a[i], prof.b[i]) == cudaSuccess) {
+        prof.ms[prof.cat[i]] += t;
+        prof.cnt[prof.cat[i]]++;
+      }
+    }
+    prof.used = 0;
+  }
 
   int init(int dev) {
     device = dev;
@@ -131,6 +181,10 @@ struct Ctx {
     if (S) cudaFree(S);
     if (S_host) cudaFreeHost(S_host);
     if (ev) cudaEventDestroy(ev);
+    if (prof.created) {
+      for (int i = 0; i < KernelProf::kN; ++i) { cudaEventDestroy(prof.a[i]); cudaEventDestroy(prof.b[i]); }
+      prof.created = false;
+    }
     if (own_stream && stream) cudaStreamDestroy(stream);
     red = RedWs{nullptr, nullptr, 0};
     S = nullptr; S_host = nullptr; ev = nullptr; stream = nullptr;

@@ -671,11 +671,13 @@ int ConeDev::normalize_box(const double *D_host) {
   if (scaled_cones) return 0;
   scaled_cones = true;
   if (bsize <= 1) return 0;
-  const double *Db = D_host ? D_host + z + l : nullptr;
-  for (int j = 0; j < bsize - 1; ++j) {
-    const double factor = Db ? Db[j + 1] / Db[0] : 1.0;
-    bu[j] = (bu[j] >= 1e15) ? INFINITY : bu[j] * factor;
-    bl[j] = (bl[j] <= -1e15) ? -INFINITY : bl[j] * factor;
+  if (D_host) {  // only when a scaling exists (cones.c:1553-1554); otherwise bounds stay as given
+    const double *Db = D_host + z + l;
+    for (int j = 0; j < bsize - 1; ++j) {
+      const double factor = Db[j + 1] / Db[0];
+      bu[j] = (bu[j] >= 1e15) ? INFINITY : bu[j] * factor;
+      bl[j] = (bl[j] <= -1e15) ? -INFINITY : bl[j] * factor;
+    }
   }
   const double one = 1.0;  // box_t_warm_start = 1, cones.c:1552
   if (h2d(*c, d_bu, bu.data(), (size_t)bsize - 1) || h2d(*c, d_bl, bl.data(), (size_t)bsize - 1) ||

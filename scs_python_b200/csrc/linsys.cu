@@ -248,26 +248,30 @@ int LinSys::update_precond() {
   return 0;
 }
 
-int LinSys::launch_A_scaled(const double *x, double *out, const int *skip) {
+int LinSys::launch_A_scaled(const double *x, double *out, const int *skip, int tag) {
   EpiScaleRy epi;
   epi.out = out; epi.ry = diag_r + n;
   ElemMul e{x};
+  const int ps = c->prof_begin(0, tag);
   row_kernel<ElemMul, ElemMul, EpiScaleRy, false>
       <<<chA.grid, kThreads, 0, c->stream>>>(A, e, A, e, chA.d, chA.n, epi, c->red, c->S, skip);
+  c->prof_end(ps);
   c->launches++; c->spmv_calls++;
   return 0;
 }
 
-int LinSys::launch_G(const double *zin, const double *pin, double *out, const int *skip) {
+int LinSys::launch_G(const double *zin, const double *pin, double *out, const int *skip, int tag) {
   EpiG epi;
   epi.Gp = out; epi.p = pin; epi.rx = diag_r;
   ElemMul ea{zin}, eb{pin};
+  const int ps = c->prof_begin(1, tag);
   if (hasP)
     row_kernel<ElemMul, ElemMul, EpiG, true>
         <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, P, eb, chAt.d, chAt.n, epi, c->red, c->S, skip);
   else
     row_kernel<ElemMul, ElemMul, EpiG, false>
         <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, P, eb, chAt.d, chAt.n, epi, c->red, c->S, skip);
+  c->prof_end(ps);
   c->launches++; c->spmv_calls++;
   return 0;
 }
@@ -316,14 +320,15 @@ int LinSys::solve_dev(double *b, const double *ws, int first_batch) {
   int its = 0;
   for (;;) {
     for (int k = 0; k < batch && enq < max_its; ++k, ++enq) {
-      launch_A_scaled(p, tmp, done);
-      launch_G(tmp, p, Gp, done);
+      launch_A_scaled(p, tmp, done, (int)enq);
+      launch_G(tmp, p, Gp, done, (int)enq);
       k_cg_update<<<gn, kThreads, 0, st>>>(b, r, z, p, Gp, M, n, cx.red, S);
       k_cg_pupdate<<<gn, kThreads, 0, st>>>(p, z, n, S);
       cx.launches += 2;
     }
     if (cx.fetch_scalars()) return -1;
     its = cx.S_host->cg_its;
+    cx.prof_flush(its);
     if (cx.S_host->cg_done || enq >= max_its) break;
     batch = batch < 32 ? batch * 2 : 64;
   }

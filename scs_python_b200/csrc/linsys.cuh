@@ -45,8 +45,8 @@ struct LinSys {
   double bytes_At() const { return 12.0 * At.nnz + 4.0 * (n + 1) + 8.0 * m + 8.0 * n; }
   double bytes_P() const { return hasP ? 12.0 * P.nnz + 4.0 * (n + 1) + 16.0 * n : 0.0; }
   // launchers shared with the ADMM driver
-  int launch_A_scaled(const double *x, double *out, const int *skip);  // out = R_y^-1 A x
-  int launch_G(const double *zin, const double *pin, double *out, const int *skip);  // out = A'z + P p + R_x p ; S->alpha
+  int launch_A_scaled(const double *x, double *out, const int *skip, int tag = -1);  // out = R_y^-1 A x
+  int launch_G(const double *zin, const double *pin, double *out, const int *skip, int tag = -1);  // out = A'z + P p + R_x p ; S->alpha
 };
 
 }  // namespace b200

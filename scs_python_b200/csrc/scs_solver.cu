@@ -537,6 +537,14 @@ struct SCS_WORK {
   int last_scale_update_iter = 0, n_log_scale_factor = 0, scale_updates = 0;
   long long admm_iters = 0;
   double alg_bytes = 0;
+  // iteration marks (bench.py)
+  int mark_begin = -1, mark_end = -1;
+  cudaEvent_t mark_ev[2] = {nullptr, nullptr};
+  ScsB200Marks marks;
+  long long mk_launch0 = 0, mk_cg0 = 0;
+  double mk_bytes0 = 0;
+  int mk_iter0 = 0;
+  bool mk_open = false, mk_done = false;
 };
 
 namespace b200 {
@@ -904,10 +912,44 @@ static int update_scale(SCS_WORK *w, int iter) {
   return 0;
 }
 
+static void mark_open(SCS_WORK *w, int iter) {
+  cudaEventRecord(w->mark_ev[0], w->c.stream);
+  w->mk_launch0 = w->c.launches;
+  w->mk_cg0 = w->ls.tot_cg_its;
+  w->mk_bytes0 = w->alg_bytes;
+  w->mk_iter0 = iter;
+  w->mk_open = true;
+  w->c.prof.used = 0;
+  for (int k = 0; k < 4; ++k) { w->c.prof.ms[k] = 0; w->c.prof.cnt[k] = 0; }
+  w->c.prof_enable(true);
+}
+static void mark_close(SCS_WORK *w, int iter) {
+  cudaEventRecord(w->mark_ev[1], w->c.stream);
+  cudaStreamSynchronize(w->c.stream);
+  w->c.prof_flush(0x7fffffff);
+  w->c.prof_enable(false);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, w->mark_ev[0], w->mark_ev[1]);
+  ScsB200Marks &mk = w->marks;
+  mk.ms = ms;
+  mk.iters = iter - w->mk_iter0;
+  mk.cg_iters = w->ls.tot_cg_its - w->mk_cg0;
+  mk.kernel_launches = w->c.launches - w->mk_launch0;
+  mk.algorithmic_bytes = w->alg_bytes - w->mk_bytes0;
+  mk.spmv_a_ms = w->c.prof.ms[0]; mk.spmv_g_ms = w->c.prof.ms[1];
+  mk.spmv_a_launches = w->c.prof.cnt[0]; mk.spmv_g_launches = w->c.prof.cnt[1];
+  mk.bytes_a = w->ls.bytes_A();
+  mk.bytes_g = w->ls.bytes_At() + w->ls.bytes_P();
+  w->mk_open = false;
+  w->mk_done = true;
+}
+
 static void free_work(SCS_WORK *w) {
   if (!w) return;
   cudaSetDevice(w->c.device);
   if (w->c.stream) cudaStreamSynchronize(w->c.stream);
+  if (w->mark_ev[0]) cudaEventDestroy(w->mark_ev[0]);
+  if (w->mark_ev[1]) cudaEventDestroy(w->mark_ev[1]);
   w->ls.destroy();
   w->cone.destroy();
   if (w->has_aa) w->aa.destroy();
@@ -1149,6 +1191,10 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   const double bytes_iter_fixed = 14.0 * l * 8.0;
   int i;
   for (i = 0; i < stgs->max_iters; ++i) {
+    if (w->mark_begin >= 0) {
+      if (i == w->mark_begin && !w->mk_open && !w->mk_done) mark_open(w, i);
+      if (i == w->mark_end && w->mk_open) mark_close(w, i);
+    }
     // ---- Anderson acceleration (scs.c:1306-1313)
     if (accel && i > 0 && i % interval == 0) {
       const int sl = w->ev.begin(2, st);
@@ -1221,6 +1267,8 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
       w->ev.flush();
     }
   }
+  if (w->mk_open) mark_close(w, i);
+  w->mark_begin = w->mark_end = -1;
   w->admm_iters += i;
   if (stgs->verbose) {
     if (populate_residuals(w, i)) return failure(w, m, n, sol, info, SCS_FAILED, "error in residuals", "failure");
@@ -1335,6 +1383,25 @@ extern "C" scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out) {
   out->algorithmic_bytes = w->alg_bytes;
   out->h2d_bytes = w->c.h2d;
   out->d2h_bytes = w->c.d2h;
+  return 0;
+}
+
+extern "C" scs_int scs_b200_set_marks(ScsWork *w, scs_int begin_iter, scs_int end_iter) {
+  if (!w || begin_iter < 0 || end_iter <= begin_iter) return -1;
+  if (cudaSetDevice(w->c.device) != cudaSuccess) return -1;
+  if (!w->mark_ev[0]) {
+    if (cudaEventCreate(&w->mark_ev[0]) != cudaSuccess || cudaEventCreate(&w->mark_ev[1]) != cudaSuccess) return -1;
+  }
+  w->mark_begin = begin_iter;
+  w->mark_end = end_iter;
+  w->mk_open = false;
+  w->mk_done = false;
+  memset(&w->marks, 0, sizeof(w->marks));
+  return 0;
+}
+extern "C" scs_int scs_b200_get_marks(const ScsWork *w, ScsB200Marks *out) {
+  if (!w || !out || !w->mk_done) return -1;
+  *out = w->marks;
   return 0;
 }
 

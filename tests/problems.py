@@ -38,29 +38,7 @@ def gen_feasible(K, n, density, seed, with_P=False):
     return data, p_star
 
 
-def gen_lasso(n0, m0, nnz_per_row, seed):
-    """Sparse LASSO in the form of the reference documentation example
-    (S/docs/src/examples/python/lasso.py:23-45): variables (x, y, t),
-    min 0.5 y'y + lam 1't  s.t. y = Ad x - b0, -t <= x <= t.
-    SCS sizes: n = 2 n0 + m0, m = m0 + 2 n0, cone z = m0, l = 2 n0."""
-    rng = np.random.RandomState(seed)
-    nnz = int(m0 * nnz_per_row)
-    rows = rng.randint(0, m0, size=nnz)
-    cols = rng.randint(0, n0, size=nnz)
-    vals = rng.randn(nnz)
-    Ad = sp.coo_matrix((vals, (rows, cols)), shape=(m0, n0)).tocsc()
-    x_true = np.where(rng.rand(n0) < 0.01, rng.randn(n0), 0.0)
-    b0 = Ad @ x_true + 0.1 * rng.randn(m0)
-    lam = 0.1 * np.max(np.abs(Ad.T @ b0))
-    In = sp.eye(n0, format="csc")
-    Im = sp.eye(m0, format="csc")
-    A = sp.bmat([[Ad, -Im, None], [In, None, -In], [-In, None, -In]], format="csc")
-    # sp.bmat with None blocks needs explicit zero blocks for the t / y columns:
-    A = sp.bmat([[Ad, -Im, sp.csc_matrix((m0, n0))],
-                 [In, sp.csc_matrix((n0, m0)), -In],
-                 [-In, sp.csc_matrix((n0, m0)), -In]], format="csc")
-    P = sp.block_diag([sp.csc_matrix((n0, n0)), Im, sp.csc_matrix((n0, n0))], format="csc")
-    b = np.concatenate([b0, np.zeros(2 * n0)])
-    c = np.concatenate([np.zeros(n0 + m0), lam * np.ones(n0)])
-    A.sort_indices()
-    return dict(A=A, P=P, b=b, c=c), dict(z=m0, l=2 * n0)
+def gen_lasso(n0, m0, nnz_per_col, seed):
+    from scs_python_b200 import problems as P
+    data, cone, _ = P.lasso(n0, m0, nnz_per_col, seed)
+    return data, cone

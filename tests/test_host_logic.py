@@ -1,0 +1,96 @@
+"""CPU tier: host-side logic -- workload builders, bench.py plumbing and the world_size-2
+rank sharding used for N > 1 (gloo)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lasso_builder_matches_scipy_assembly():
+    from scs_python_b200 import problems
+    n0, m0, k = 50, 100, 7
+    data, cone, aux = problems.lasso(n0, m0, k, seed=3)
+    A = data["A"]
+    assert A.shape == (m0 + 2 * n0, 2 * n0 + m0) and cone == dict(z=m0, l=2 * n0)
+    assert A.nnz == n0 * k + m0 + 4 * n0
+    B = A.copy(); B.sort_indices()
+    assert np.array_equal(A.indices, B.indices) and np.array_equal(A.indptr, B.indptr)  # already sorted CSC
+    Ad = A[:m0, :n0]
+    assert np.all(np.diff(Ad.indptr) == k)
+    for j in range(n0):
+        rows = Ad.indices[Ad.indptr[j]:Ad.indptr[j + 1]]
+        assert len(set(rows.tolist())) == k
+    I_n, I_m = sp.eye(n0, format="csc"), sp.eye(m0, format="csc")
+    ref = sp.bmat([[Ad, -I_m, sp.csc_matrix((m0, n0))], [I_n, sp.csc_matrix((n0, m0)), -I_n],
+                   [-I_n, sp.csc_matrix((n0, m0)), -I_n]], format="csc")
+    assert abs(A - ref).max() == 0.0
+    P = data["P"]
+    assert abs(P - sp.block_diag([sp.csc_matrix((n0, n0)), I_m, sp.csc_matrix((n0, n0))])).max() == 0.0
+    assert np.allclose(data["c"][n0 + m0:], aux["lam"]) and np.all(data["c"][:n0 + m0] == 0)
+
+
+def test_lasso_builder_is_seeded():
+    from scs_python_b200 import problems
+    a, _, _ = problems.lasso(20, 40, 5, seed=1)
+    b, _, _ = problems.lasso(20, 40, 5, seed=1)
+    c, _, _ = problems.lasso(20, 40, 5, seed=2)
+    assert abs(a["A"] - b["A"]).max() == 0 and abs(a["A"] - c["A"]).max() > 0
+
+
+def test_gen_feasible_is_feasible():
+    from oracle import scs_oracle as O
+    from tests import problems
+    K = dict(z=2, l=3, q=[3], s=[2], ep=1, ed=1, p=[0.4])
+    data, p_star = problems.gen_feasible(K, 6, 0.5, seed=4)
+    sol = O.ScsOracle(data, K, eps_abs=1e-8, eps_rel=1e-8).solve()
+    assert sol["info"]["status_val"] == 1 and abs(sol["info"]["pobj"] - p_star) < 1e-5
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as td
+import bench
+td.init_process_group(backend="gloo")
+rank, world = td.get_rank(), td.get_world_size()
+dev = torch.device("cpu")
+# every rank owns its own problem instance (seed + rank): no data-path collective
+data, cone, desc = bench.workload(0.001, seed=rank)
+iters, ms = 25 * 4, 10.0 * (rank + 1)
+tot = bench.sum_over_ranks(td, dev, iters)
+mx = bench.max_over_ranks(td, dev, ms)
+if rank == 0:
+    import json
+    print(json.dumps(dict(world=world, total_iters=tot, max_ms=mx, value=tot / (mx * 1e-3), nnz=desc["nnz_A"])))
+td.barrier()
+td.destroy_process_group()
+'''
+
+
+def test_rank_sharding_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % dict(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29631", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["world"] == 2 and out["total_iters"] == 200 and out["max_ms"] == 20.0
+    assert abs(out["value"] - 200 / 0.020) < 1e-6   # whole-job iterations / slowest rank
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` is CPU-only and must print one JSON line (tiny scale here)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup",
+                        "1", "--scale", "0.002", "--iters-per-step", "5"], capture_output=True, text=True, timeout=600,
+                       cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["impl"] == "reference" and out["metric"] == "admm_iters_per_sec" and out["value"] > 0
+    assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["cpu_baseline"]["kind"] in ("reference", "port")
