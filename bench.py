@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 FULL = dict(n0=1_000_000, m0=2_000_000, nnz_per_col=100)
+GATHER_CEILING_GELEMS = 272.0  # measured on B200: tools/probes/gather_probe.cu, profiles/r1b_gather_probe_x8MB.txt
 
 
 def parse_args():
@@ -303,6 +304,9 @@ def run_b200(args):
     clocks = sampler.stop()
     mk = inner.get_marks()
     assert mk is not None and mk["iters"] == K * ips, "timed region did not cover exactly K steps: %s" % (mk,)
+    # the same two kernels, back-to-back launches bracketed by CUDA events on the solve stream
+    iso_a_ms, _ = inner.bench_spmv(0, 20)
+    iso_g_ms, _ = inner.bench_spmv(1, 20)
     ms_max = max_over_ranks(td, local, mk["ms"])
     total_iters = sum_over_ranks(td, local, mk["iters"])
     value = total_iters / (ms_max * 1e-3)
@@ -336,12 +340,22 @@ def run_b200(args):
         g_ms = mk["spmv_g_ms"] / max(1, mk["spmv_g_launches"])
         a_ms = mk["spmv_a_ms"] / max(1, mk["spmv_a_launches"])
         ach = mk["bytes_g"] / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
+        nnz_g = desc["nnz_A"] + desc["nnz_P"]
         roofline = dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=ncu_traffic(),
                         kernel="row_kernel<ElemMul,ElemMul,EpiG,DUAL> (Gp = A' z + P p + R_x p, p'Gp fused)",
                         avg_launch_ms=g_ms, launches_timed=int(mk["spmv_g_launches"]),
+                        timing="device %globaltimer, first CTA start -> last CTA end, every launch inside the timed "
+                               "region (graph WHILE-body launches cannot carry CUDA events)",
+                        isolated_event_ms=iso_g_ms,
+                        isolated_event_achieved=(mk["bytes_g"] / (iso_g_ms * 1e-3) / 1e9 if iso_g_ms > 0 else 0.0),
                         algorithmic_bytes_per_launch=mk["bytes_g"], peak_source=peak_src,
+                        gather_ceiling_gelem_s=GATHER_CEILING_GELEMS,
+                        gather_ceiling_frac=(nnz_g / (g_ms * 1e-3) / 1e9 / GATHER_CEILING_GELEMS if g_ms > 0 else 0.0),
+                        gather_note="one random FP64 operand per stored non-zero: 32 B L2 sector per 8 B; measured "
+                                    "ceiling 272 G gathers/s on B200 (profiles/r1b_gather_probe_*.txt, DESIGN.md 3.1)",
                         second_kernel=dict(kernel="row_kernel<ElemMul,ElemMul,EpiScaleRy> (z = R_y^-1 A p)",
                                            avg_launch_ms=a_ms, launches_timed=int(mk["spmv_a_launches"]),
+                                           isolated_event_ms=iso_a_ms,
                                            achieved=(mk["bytes_a"] / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0)),
                         iteration_model=dict(algorithmic_bytes=mk["algorithmic_bytes"],
                                              achieved=mk["algorithmic_bytes"] / (mk["ms"] * 1e-3) / 1e9,
@@ -361,11 +375,13 @@ def run_b200(args):
     # ---- time to eps = 1e-4 (the second half of BASELINE.json's metric), rank 0 only
     if rank == 0 and not args.no_time_to_eps:
         t = time.perf_counter()
-        s2 = scsb.SCS(data, cone, verbose=False, max_iters=5000)
+        # eps_infeas: with the default 1e-7 the REFERENCE itself stops at iteration 0 with a false
+        # "unbounded" certificate on the full-size instance; 1e-12 in both arms.
+        s2 = scsb.SCS(data, cone, verbose=False, max_iters=5000, eps_infeas=1e-12)
         r2 = s2.solve(warm_start=False)
         wall = time.perf_counter() - t
         i2 = r2["info"]
-        out["time_to_eps"] = dict(eps=1e-4, status=i2["status"], iters=i2["iter"], setup_ms=i2["setup_time"],
+        out["time_to_eps"] = dict(eps=1e-4, eps_infeas=1e-12, status=i2["status"], iters=i2["iter"], setup_ms=i2["setup_time"],
                                   solve_ms=i2["solve_time"], wall_s_incl_upload=wall, pobj=i2["pobj"], dobj=i2["dobj"],
                                   res_pri=i2["res_pri"], res_dual=i2["res_dual"], gap=i2["gap"])
         s2._solver.finish()

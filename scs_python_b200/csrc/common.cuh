@@ -79,6 +79,17 @@ struct DevScalars {
   // --- misc results of setup / finalisation reductions ---
   double sigma;      // primal_scale == dual_scale (normalize.c:46-60)
   double fin[4];     // ||s||_inf, ||y||_inf, s'y of the un-normalised solution (scs.c:885-887)
+  // --- device-side loop control of the graph-launched ADMM iteration ---
+  int iter;          // ADMM iteration index, advanced by the dual-step kernel
+  int cg_max_its;    // 10 n (private.c:299)
+  // phase clocks in ns of %globaltimer: [0] lin-sys, [1] cones, [2] acceleration
+  unsigned long long t_mark;
+  unsigned long long phase_ns[4];
+  // in-region device timing of the two CG SpMV kernels (bench marks): [0] z = R_y^-1 A p,
+  // [1] Gp = A'z + P p + R_x p.  Start = first CTA's first instruction, end = last CTA done.
+  int kt_on, kt_pad;
+  unsigned int kt_ticket[2], kt_cnt[2];
+  unsigned long long kt_start[2], kt_ns[2];
 };
 
 // indices into DevScalars::res
@@ -92,19 +103,6 @@ enum ResIdx {
   R_COUNT
 };
 
-// Optional per-launch CUDA-event timing of the SpMV kernels (bench.py roofline): events are
-// recorded on the launching stream inside the timed region; launches enqueued after CG had
-// already converged (no-op early exits) are recognised by their tag and left out.
-struct KernelProf {
-  static constexpr int kN = 1024;
-  bool on = false, created = false;
-  cudaEvent_t a[kN], b[kN];
-  int cat[kN], tag[kN];
-  int used = 0;
-  double ms[4] = {0, 0, 0, 0};
-  long long cnt[4] = {0, 0, 0, 0};
-};
-
 struct Ctx {
   int device = 0;
   int sms = 148;
@@ -116,44 +114,7 @@ struct Ctx {
   cudaEvent_t ev = nullptr;
   // counters
   long long launches = 0, spmv_calls = 0, h2d = 0, d2h = 0;
-  KernelProf prof;
   int grid_ew() const { return sms * kCtasPerSm; }
-
-  int prof_enable(bool on) {
-    if (on && !prof.created) {
-      for (int i = 0; i < KernelProf::kN; ++i) {
-        CUDA_OK(cudaEventCreate(&prof.a[i]));
-        CUDA_OK(cudaEventCreate(&prof.b[i]));
-      }
-      prof.created = true;
-    }
-    prof.on = on;
-    return 0;
-  }
-  // tag: CG iteration index of the launch inside the current solve, or -1 (always real)
-  int prof_begin(int category, int tag) {
-    if (!prof.on || prof.used >= KernelProf::kN) return -1;
-    const int s = prof.used++;
-    prof.cat[s] = category;
-    prof.tag[s] = tag;
-    cudaEventRecord(prof.a[s], stream);
-    return s;
-  }
-  void prof_end(int slot) {
-    if (slot >= 0) cudaEventRecord(prof.b[slot], stream);
-  }
-  // call right after a stream synchronisation; real_its = CG iterations actually executed
-  void prof_flush(int real_its) {
-    for (int i = 0; i < prof.used; ++i) {
-      if (prof.tag[i] >= 0 && prof.tag[i] >= real_its) continue;
-      float t = 0.f;
-      if (cudaEventElapsedTime(&t, prof.a[i], prof.b[i]) == cudaSuccess) {
-        prof.ms[prof.cat[i]] += t;
-        prof.cnt[prof.cat[i]]++;
-      }
-    }
-    prof.used = 0;
-  }
 
   int init(int dev) {
     device = dev;
@@ -181,10 +142,6 @@ struct Ctx {
     if (S) cudaFree(S);
     if (S_host) cudaFreeHost(S_host);
     if (ev) cudaEventDestroy(ev);
-    if (prof.created) {
-      for (int i = 0; i < KernelProf::kN; ++i) { cudaEventDestroy(prof.a[i]); cudaEventDestroy(prof.b[i]); }
-      prof.created = false;
-    }
     if (own_stream && stream) cudaStreamDestroy(stream);
     red = RedWs{nullptr, nullptr, 0};
     S = nullptr; S_host = nullptr; ev = nullptr; stream = nullptr;
@@ -237,6 +194,40 @@ inline int d2h(Ctx &c, T *dst, const T *src, size_t count) {
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ device helpers ----
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void kt_begin(DevScalars *S, int cat) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && S->kt_on) S->kt_start[cat] = gtimer();
+}
+// by the one thread that knows the grid is done (finaliser of a grid reduction)
+__device__ __forceinline__ void kt_end_last(DevScalars *S, int cat) {
+  if (S->kt_on) {
+    S->kt_ns[cat] += gtimer() - S->kt_start[cat];
+    S->kt_cnt[cat] += 1;
+  }
+}
+// by every thread of a kernel without a grid reduction: ticket to find the last CTA
+__device__ __forceinline__ void kt_end_ticket(DevScalars *S, int cat) {
+  if (!S->kt_on) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&S->kt_ticket[cat], 1u) == gridDim.x - 1) {
+      S->kt_ticket[cat] = 0u;
+      kt_end_last(S, cat);
+    }
+  }
+}
+// Close the running phase interval into phase_ns[slot] and start the next one.  Called by one
+// thread of a kernel that sits on a phase boundary of the ADMM iteration.
+__device__ __forceinline__ void phase_lap(DevScalars *S, int slot) {
+  const unsigned long long now = gtimer();
+  if (slot >= 0) S->phase_ns[slot] += now - S->t_mark;
+  S->t_mark = now;
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

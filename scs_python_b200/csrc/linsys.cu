@@ -3,6 +3,12 @@
 
 namespace b200 {
 
+// Inside the graph-launched iteration the CG loop is a WHILE conditional node: the kernels
+// that decide convergence also set the loop condition.  use_h == 0 on the stream path.
+__device__ __forceinline__ void cg_set_loop(const CgCtl &c, int keep_going) {
+  if (c.use_h) cudaGraphSetConditional(c.h, keep_going ? 1u : 0u);
+}
+
 // ------------------------------------------------------------------------- epilogues ---
 // b[j] += (A' tmp)_j                                     (private.c:297)
 struct EpiRhs : EpiNoState {
@@ -10,10 +16,16 @@ struct EpiRhs : EpiNoState {
   __device__ __forceinline__ void row(State &, int j, double acc) const { b[j] += acc; }
 };
 // out[i] = (A x)_i / R_y,i                               (private.c:116-117)
-struct EpiScaleRy : EpiNoState {
+struct EpiScaleRy {
+  static constexpr bool kSeparate = false;
+  struct State {};
   double *out;
   const double *ry;  // diag_r + n
+  DevScalars *S_;
+  __device__ __forceinline__ void row2(State &, int, double, double) const {}
+  __device__ __forceinline__ void init(State &) const { kt_begin(S_, 0); }
   __device__ __forceinline__ void row(State &, int i, double acc) const { out[i] = acc / ry[i]; }
+  __device__ __forceinline__ void finish(State &, const RedWs &, DevScalars *S) const { kt_end_ticket(S, 0); }
 };
 // Gp_j = (A' z)_j + (P p)_j + R_x,j p_j ; p'Gp ; alpha = z'r / p'Gp     (private.c:181-183)
 struct EpiG {
@@ -22,7 +34,8 @@ struct EpiG {
   __device__ __forceinline__ void row2(State &, int, double, double) const {}
   double *Gp;
   const double *p, *rx;
-  __device__ __forceinline__ void init(State &s) const { s.pgp = 0.0; }
+  DevScalars *S_;
+  __device__ __forceinline__ void init(State &s) const { s.pgp = 0.0; kt_begin(S_, 1); }
   __device__ __forceinline__ void row(State &s, int j, double acc) const {
     const double pj = p[j];
     const double g = acc + rx[j] * pj;
@@ -34,6 +47,7 @@ struct EpiG {
     grid_reduce<1, 0>(v, ws, [S](double *o) {
       S->pGp = o[0];
       S->alpha = S->ztr / o[0];
+      kt_end_last(S, 1);
     });
   }
 };
@@ -46,6 +60,7 @@ struct EpiG0 {
   double *b;  // in: rhs, out: x = s
   const double *s, *rx, *M;
   double *r, *z, *p;
+  CgCtl ctl;
   __device__ __forceinline__ void init(State &st) const { st.ztr = 0.0; st.nr = 0.0; }
   __device__ __forceinline__ void row(State &st, int j, double acc) const {
     const double sj = s[j];
@@ -60,10 +75,13 @@ struct EpiG0 {
   }
   __device__ __forceinline__ void finish(State &st, const RedWs &ws, DevScalars *S) const {
     double v[2] = {st.ztr, st.nr};
-    grid_reduce<1, 1>(v, ws, [S](double *o) {
+    const CgCtl cc = ctl;
+    grid_reduce<1, 1>(v, ws, [S, cc](double *o) {
       S->ztr = o[0];
       S->norm_r = o[1];
-      S->cg_done = (o[1] < fmax(S->cg_tol, 1e-12)) ? 1 : 0;
+      const int done = (o[1] < fmax(S->cg_tol, 1e-12)) ? 1 : 0;
+      S->cg_done = done;
+      cg_set_loop(cc, !done);
     });
   }
 };
@@ -92,7 +110,7 @@ k_scale_ry(const double *__restrict__ by, const double *__restrict__ ry, double 
 // cold start of CG (s == NULL): r = b ; x = 0 ; z = M r ; p = z      (private.c:147-152,170-174)
 __global__ void __launch_bounds__(kThreads)
 k_cg_init_cold(double *__restrict__ b, const double *__restrict__ M, double *__restrict__ r,
-               double *__restrict__ z, double *__restrict__ p, int n, RedWs ws, DevScalars *S) {
+               double *__restrict__ z, double *__restrict__ p, int n, RedWs ws, DevScalars *S, CgCtl ctl) {
   if (S->cg_done) return;
   double v[2] = {0.0, 0.0};
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -105,10 +123,12 @@ k_cg_init_cold(double *__restrict__ b, const double *__restrict__ M, double *__r
     v[0] = fma(zj, rj, v[0]);
     v[1] = fmax(v[1], fabs(rj));
   }
-  grid_reduce<1, 1>(v, ws, [S](double *o) {
+  grid_reduce<1, 1>(v, ws, [S, ctl](double *o) {
     S->ztr = o[0];
     S->norm_r = o[1];
-    S->cg_done = (o[1] < fmax(S->cg_tol, 1e-12)) ? 1 : 0;
+    const int done = (o[1] < fmax(S->cg_tol, 1e-12)) ? 1 : 0;
+    S->cg_done = done;
+    cg_set_loop(ctl, !done);
   });
 }
 
@@ -116,7 +136,7 @@ k_cg_init_cold(double *__restrict__ b, const double *__restrict__ M, double *__r
 //                                                       (private.c:184-213)
 __global__ void __launch_bounds__(kThreads)
 k_cg_update(double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, const double *__restrict__ p,
-            const double *__restrict__ Gp, const double *__restrict__ M, int n, RedWs ws, DevScalars *S) {
+            const double *__restrict__ Gp, const double *__restrict__ M, int n, RedWs ws, DevScalars *S, CgCtl ctl) {
   if (S->cg_done) return;
   const double alpha = S->alpha;
   double v[2] = {0.0, 0.0};
@@ -129,14 +149,17 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, double *__restrict__
     v[0] = fma(zj, rj, v[0]);
     v[1] = fmax(v[1], fabs(rj));
   }
-  grid_reduce<1, 1>(v, ws, [S](double *o) {
+  grid_reduce<1, 1>(v, ws, [S, ctl](double *o) {
     const double ztr_prev = S->ztr;
-    S->cg_its += 1;
+    const int its = S->cg_its + 1;
+    S->cg_its = its;
     S->cg_its_total += 1;
     S->norm_r = o[1];
     S->ztr = o[0];
     S->beta = o[0] / ztr_prev;
-    if (o[1] < S->cg_tol || ztr_prev == 0.0 || !(o[1] == o[1])) S->cg_done = 1;
+    const int done = (o[1] < S->cg_tol || ztr_prev == 0.0 || !(o[1] == o[1]) || its >= S->cg_max_its) ? 1 : 0;
+    if (done) S->cg_done = 1;
+    cg_set_loop(ctl, !done);
   });
 }
 
@@ -200,6 +223,12 @@ int LinSys::init(Ctx *ctx, const ScsMatrix *Ah, const ScsMatrix *Ph) {
   if (c->sync()) return -1;
   if (chunks_build(*c, chA, A, nullptr)) return -1;
   if (chunks_build(*c, chAt, At, hasP ? &P : nullptr)) return -1;
+  {
+    const long long mi = 10ll * n;  // private.c:299
+    const int mi32 = mi > 0x7fffffffLL ? 0x7fffffff : (int)mi;
+    CUDA_OK(cudaMemcpyAsync(&c->S->cg_max_its, &mi32, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
   if (dev_alloc_zero(&M, (size_t)n, c->stream) || dev_alloc_zero(&p, (size_t)n, c->stream) ||
       dev_alloc_zero(&r, (size_t)n, c->stream) || dev_alloc_zero(&Gp, (size_t)n, c->stream) ||
       dev_alloc_zero(&z, (size_t)n, c->stream) || dev_alloc_zero(&tmp, (size_t)m, c->stream))
@@ -248,31 +277,29 @@ int LinSys::update_precond() {
   return 0;
 }
 
-int LinSys::launch_A_scaled(const double *x, double *out, const int *skip, int tag) {
+int LinSys::launch_A_scaled(const double *x, double *out, const int *skip, int tag, bool counted) {
   EpiScaleRy epi;
-  epi.out = out; epi.ry = diag_r + n;
+  epi.out = out; epi.ry = diag_r + n; epi.S_ = c->S;
   ElemMul e{x};
-  const int ps = c->prof_begin(0, tag);
+  (void)tag;
   row_kernel<ElemMul, ElemMul, EpiScaleRy, false>
       <<<chA.grid, kThreads, 0, c->stream>>>(A, e, A, e, chA.d, chA.n, epi, c->red, c->S, skip);
-  c->prof_end(ps);
-  c->launches++; c->spmv_calls++;
+  if (counted) { c->launches++; c->spmv_calls++; }
   return 0;
 }
 
-int LinSys::launch_G(const double *zin, const double *pin, double *out, const int *skip, int tag) {
+int LinSys::launch_G(const double *zin, const double *pin, double *out, const int *skip, int tag, bool counted) {
   EpiG epi;
-  epi.Gp = out; epi.p = pin; epi.rx = diag_r;
+  epi.Gp = out; epi.p = pin; epi.rx = diag_r; epi.S_ = c->S;
   ElemMul ea{zin}, eb{pin};
-  const int ps = c->prof_begin(1, tag);
+  (void)tag;
   if (hasP)
     row_kernel<ElemMul, ElemMul, EpiG, true>
         <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, P, eb, chAt.d, chAt.n, epi, c->red, c->S, skip);
   else
     row_kernel<ElemMul, ElemMul, EpiG, false>
         <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, P, eb, chAt.d, chAt.n, epi, c->red, c->S, skip);
-  c->prof_end(ps);
-  c->launches++; c->spmv_calls++;
+  if (counted) { c->launches++; c->spmv_calls++; }
   return 0;
 }
 
@@ -282,7 +309,7 @@ int LinSys::prepare_flags(const double *b, double tol) {
   return 0;
 }
 
-int LinSys::solve_dev(double *b, const double *ws, int first_batch) {
+int LinSys::enqueue_head(double *b, const double *ws, CgCtl ctl) {
   Ctx &cx = *c;
   DevScalars *S = cx.S;
   const int *done = &S->cg_done;
@@ -300,7 +327,7 @@ int LinSys::solve_dev(double *b, const double *ws, int first_batch) {
   if (ws) {
     launch_A_scaled(ws, tmp, done);
     EpiG0 epi;
-    epi.b = b; epi.s = ws; epi.rx = diag_r; epi.M = M; epi.r = r; epi.z = z; epi.p = p;
+    epi.b = b; epi.s = ws; epi.rx = diag_r; epi.M = M; epi.r = r; epi.z = z; epi.p = p; epi.ctl = ctl;
     ElemMul ea{tmp}, eb{ws};
     if (hasP)
       row_kernel<ElemMul, ElemMul, EpiG0, true>
@@ -310,39 +337,63 @@ int LinSys::solve_dev(double *b, const double *ws, int first_batch) {
           <<<chAt.grid, kThreads, 0, st>>>(At, ea, P, eb, chAt.d, chAt.n, epi, cx.red, S, done);
     cx.launches++; cx.spmv_calls++;
   } else {
-    k_cg_init_cold<<<gn, kThreads, 0, st>>>(b, M, r, z, p, n, cx.red, S);
+    k_cg_init_cold<<<gn, kThreads, 0, st>>>(b, M, r, z, p, n, cx.red, S, ctl);
     cx.launches++;
   }
+  return 0;
+}
+
+int LinSys::enqueue_cg_iter(double *b, CgCtl ctl, int tag) {
+  Ctx &cx = *c;
+  DevScalars *S = cx.S;
+  const int *done = &S->cg_done;
+  const int gn = ew_grid(cx, n);
+  // not added to cx.launches: the number of CG iterations that really execute is decided on
+  // the device (S->cg_its_total); launch totals are 4 * that counter + cx.launches
+  launch_A_scaled(p, tmp, done, tag, false);
+  launch_G(tmp, p, Gp, done, tag, false);
+  k_cg_update<<<gn, kThreads, 0, cx.stream>>>(b, r, z, p, Gp, M, n, cx.red, S, ctl);
+  k_cg_pupdate<<<gn, kThreads, 0, cx.stream>>>(p, z, n, S);
+  return 0;
+}
+
+int LinSys::enqueue_tail(double *b) {
+  // y = R_y^-1 (A x - ry), or everything zero
+  Ctx &cx = *c;
+  DevScalars *S = cx.S;
+  EpiY epi; epi.by = b + n; epi.ry = diag_r + n;
+  ElemMul e{b};
+  row_kernel<ElemMul, ElemMul, EpiY, false>
+      <<<chA.grid, kThreads, 0, cx.stream>>>(A, e, A, e, chA.d, chA.n, epi, cx.red, S, &S->zero_rhs);
+  k_zero_if<<<ew_grid(cx, n + m), kThreads, 0, cx.stream>>>(b, n + m, &S->zero_rhs);
+  cx.launches += 2; cx.spmv_calls++;
+  return 0;
+}
+
+// host-driven CG loop: enqueue a batch of iterations (kernels launched after convergence
+// return at once), read the stop flag, repeat
+int LinSys::solve_dev_loop(double *b, int first_batch) {
+  Ctx &cx = *c;
+  const CgCtl none{};
   const long long max_its = 10ll * n;  // private.c:299
   int batch = first_batch > 0 ? first_batch : (last_its + 1 < 1 ? 1 : last_its + 1);
   if (batch > 64) batch = 64;
   long long enq = 0;
   int its = 0;
   for (;;) {
-    for (int k = 0; k < batch && enq < max_its; ++k, ++enq) {
-      launch_A_scaled(p, tmp, done, (int)enq);
-      launch_G(tmp, p, Gp, done, (int)enq);
-      k_cg_update<<<gn, kThreads, 0, st>>>(b, r, z, p, Gp, M, n, cx.red, S);
-      k_cg_pupdate<<<gn, kThreads, 0, st>>>(p, z, n, S);
-      cx.launches += 2;
-    }
+    for (int k = 0; k < batch && enq < max_its; ++k, ++enq) enqueue_cg_iter(b, none, (int)enq);
     if (cx.fetch_scalars()) return -1;
     its = cx.S_host->cg_its;
-    cx.prof_flush(its);
     if (cx.S_host->cg_done || enq >= max_its) break;
     batch = batch < 32 ? batch * 2 : 64;
   }
   if (first_batch <= 0) last_its = its;
   tot_cg_its += its;
-  // y = R_y^-1 (A x - ry), or everything zero
-  {
-    EpiY epi; epi.by = b + n; epi.ry = diag_r + n;
-    ElemMul e{b};
-    row_kernel<ElemMul, ElemMul, EpiY, false>
-        <<<chA.grid, kThreads, 0, st>>>(A, e, A, e, chA.d, chA.n, epi, cx.red, S, &S->zero_rhs);
-    k_zero_if<<<ew_grid(cx, n + m), kThreads, 0, st>>>(b, n + m, &S->zero_rhs);
-  }
-  cx.launches += 2; cx.spmv_calls++;
+  return 0;
+}
+
+int LinSys::solve_dev(double *b, const double *ws, int first_batch) {
+  if (enqueue_head(b, ws, CgCtl{}) || solve_dev_loop(b, first_batch) || enqueue_tail(b)) return -1;
   CUDA_OK(cudaGetLastError());
   return 0;
 }

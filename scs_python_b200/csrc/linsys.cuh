@@ -14,6 +14,12 @@
 
 namespace b200 {
 
+// loop control of the CG WHILE node (zero-initialised == stream path, no graph)
+struct CgCtl {
+  cudaGraphConditionalHandle h = 0;
+  int use_h = 0;
+};
+
 struct LinSys {
   Ctx *c = nullptr;
   int n = 0, m = 0;
@@ -38,6 +44,12 @@ struct LinSys {
   // null.  Before the call the caller must have set S->cg_tol, S->zero_rhs and
   // S->cg_done (= zero_rhs).  first_batch <= 0 picks the adaptive default.
   int solve_dev(double *b, const double *ws, int first_batch);
+  // the three pieces of solve_dev, enqueue-only (no host synchronisation): used directly when
+  // the ADMM iteration is captured into a CUDA graph whose CG loop is a WHILE node
+  int enqueue_head(double *b, const double *ws, CgCtl ctl);  // tmp = ry/R_y ; b_x += A' tmp ; CG start
+  int enqueue_cg_iter(double *b, CgCtl ctl, int tag);         // one CG iteration (4 kernels)
+  int enqueue_tail(double *b);                                // y recovery / zero right-hand side
+  int solve_dev_loop(double *b, int first_batch);             // host-driven CG loop between head and tail
   // sets S->cg_tol = tol and the zero-rhs flags from ||b||_inf (device reduction)
   int prepare_flags(const double *b, double tol);
   // algorithmic bytes
@@ -45,8 +57,9 @@ struct LinSys {
   double bytes_At() const { return 12.0 * At.nnz + 4.0 * (n + 1) + 8.0 * m + 8.0 * n; }
   double bytes_P() const { return hasP ? 12.0 * P.nnz + 4.0 * (n + 1) + 16.0 * n : 0.0; }
   // launchers shared with the ADMM driver
-  int launch_A_scaled(const double *x, double *out, const int *skip, int tag = -1);  // out = R_y^-1 A x
-  int launch_G(const double *zin, const double *pin, double *out, const int *skip, int tag = -1);  // out = A'z + P p + R_x p ; S->alpha
+  int launch_A_scaled(const double *x, double *out, const int *skip, int tag = -1, bool counted = true);  // out = R_y^-1 A x
+  int launch_G(const double *zin, const double *pin, double *out, const int *skip, int tag = -1,
+               bool counted = true);  // out = A'z + P p + R_x p ; S->alpha
 };
 
 }  // namespace b200

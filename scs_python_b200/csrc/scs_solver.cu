@@ -197,9 +197,11 @@ k_warm_start(double *__restrict__ v, const double *__restrict__ x, const double 
 template <bool ACCEL>
 __global__ void __launch_bounds__(kThreads)
 k_prep(double *__restrict__ v, double *__restrict__ v_prev, double *__restrict__ u_t, const double *__restrict__ u,
-       const double *__restrict__ g, const double *__restrict__ R, double *__restrict__ ws, int n, int m, int it,
+       const double *__restrict__ g, const double *__restrict__ R, double *__restrict__ ws, int n, int m,
        RedWs red, DevScalars *S) {
   const int l = n + m + 1;
+  const int it = S->iter;
+  if (blockIdx.x == 0 && threadIdx.x == 0) phase_lap(S, -1);  // lin-sys interval starts
   double sc = 1.0;
   if (it >= kFeasibleIters) {
     const double vn = sqrt(S->vnorm2);
@@ -240,7 +242,8 @@ k_prep(double *__restrict__ v, double *__restrict__ v_prev, double *__restrict__
 // root_plus (scs.c:667-688): p = u_t (after the solve), mu = v, eta = v[l-1]
 __global__ void __launch_bounds__(kThreads)
 k_rootplus(const double *__restrict__ u_t, const double *__restrict__ v, const double *__restrict__ g,
-           const double *__restrict__ R, int nm, int it, RedWs red, DevScalars *S) {
+           const double *__restrict__ R, int nm, RedWs red, DevScalars *S) {
+  const int it = S->iter;
   double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nm; j += gridDim.x * blockDim.x) {
     const double ri = R[j], gi = g[j], pi = u_t[j], mui = v[j];
@@ -261,6 +264,7 @@ k_rootplus(const double *__restrict__ u_t, const double *__restrict__ v, const d
       const double rad = b * b - 4 * a * c;
       S->tau = (-b + sqrt(fmax(rad, 0.0))) / (2 * a);
     }
+    phase_lap(S, 0);  // lin-sys interval ends, cone interval starts
   });
 }
 
@@ -268,9 +272,10 @@ k_rootplus(const double *__restrict__ u_t, const double *__restrict__ v, const d
 // s saved in rsk (scratch until k_post overwrites it)
 __global__ void __launch_bounds__(kThreads)
 k_pre(double *__restrict__ u_t, double *__restrict__ u, double *__restrict__ rsk, const double *__restrict__ v,
-      const double *__restrict__ g, const double *__restrict__ R, int n, int m, int z, int zl, int it,
+      const double *__restrict__ g, const double *__restrict__ R, int n, int m, int z, int zl,
       const DevScalars *S) {
   const int l = n + m + 1;
+  const int it = S->iter;
   const double tau = S->tau;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x) {
     const double ut = (j < l - 1) ? fma(-tau, g[j], u_t[j]) : tau;
@@ -299,6 +304,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_post(double *__restrict__ v, double *__restrict__ rsk, const double *__restrict__ u, const double *__restrict__ u_t,
        const double *__restrict__ R, int l, double alpha, RedWs red, DevScalars *S) {
+  if (MODE != 2 && blockIdx.x == 0 && threadIdx.x == 0) phase_lap(S, 1);  // cone interval ends
   double s[1] = {0.0};
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x) {
     const double vj = v[j], uj = u[j], utj = u_t[j];
@@ -309,8 +315,15 @@ k_post(double *__restrict__ v, double *__restrict__ rsk, const double *__restric
       s[0] = fma(vn, vn, s[0]);
     }
   }
-  if (MODE != 1) grid_reduce<1, 0>(s, red, [S](double *o) { S->vnorm2 = o[0]; });
+  if (MODE != 1)
+    grid_reduce<1, 0>(s, red, [S](double *o) {
+      S->vnorm2 = o[0];
+      S->iter += 1;  // the iteration index lives on the device: the graph re-launches unchanged
+    });
 }
+
+// phase clock boundary around the acceleration kernels: slot < 0 opens, slot >= 0 closes
+__global__ void k_stamp(DevScalars *S, int slot) { phase_lap(S, slot); }
 
 // v <- rsk / R+ + 2 u_t - u after a scale update (scs.c:1180-1186)
 __global__ void __launch_bounds__(kThreads)
@@ -467,48 +480,6 @@ static void compute_residuals_h(HostResid &r, double pd) {
   if (r.bty_tau < -tol) r.res_infeas = safediv_pos_h(r.nm_aty, -r.bty_tau);
 }
 
-struct EventAccum {  // CUDA-event phase timers for info.{lin_sys,cone,accel}_time
-  static constexpr int kSlots = 48;
-  cudaEvent_t a[kSlots], b[kSlots];
-  int cat[kSlots];
-  int used = 0;
-  double total[3] = {0, 0, 0};
-  bool ok = false;
-  int init() {
-    for (int i = 0; i < kSlots; ++i) {
-      CUDA_OK(cudaEventCreate(&a[i]));
-      CUDA_OK(cudaEventCreate(&b[i]));
-    }
-    ok = true;
-    return 0;
-  }
-  void destroy() {
-    if (!ok) return;
-    for (int i = 0; i < kSlots; ++i) { cudaEventDestroy(a[i]); cudaEventDestroy(b[i]); }
-    ok = false;
-  }
-  // the caller guarantees the stream has been synchronised after the recorded events
-  void flush() {
-    for (int i = 0; i < used; ++i) {
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, a[i], b[i]) == cudaSuccess) total[cat[i]] += ms;
-    }
-    used = 0;
-  }
-  int begin(int category, cudaStream_t st) {
-    if (used >= kSlots) return -1;
-    cat[used] = category;
-    cudaEventRecord(a[used], st);
-    return used;
-  }
-  void end(int slot, cudaStream_t st) {
-    if (slot < 0) return;
-    cudaEventRecord(b[slot], st);
-    used = slot + 1;
-  }
-  void reset() { used = 0; total[0] = total[1] = total[2] = 0; }
-};
-
 }  // namespace b200
 
 using namespace b200;
@@ -519,8 +490,14 @@ struct SCS_WORK {
   ConeDev cone;
   AaDev aa;
   bool has_aa = false;
-  EventAccum ev;
   int n = 0, m = 0, l = 0;
+  // the graph-launched front half of one ADMM iteration (k_prep .. cones), CG loop = WHILE node
+  bool use_graph = false;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  cudaStream_t st_body = nullptr;
+  long long graph_launches = 0, graph_spmv = 0;  // fixed (non-CG-loop) kernels per graph launch
+  long long n_checks = 0, n_aa = 0;               // residual checks / AA applications so far
   ScsSettings stgs;
   std::string write_fn, csv_fn;
   // device state
@@ -536,7 +513,6 @@ struct SCS_WORK {
   double sum_log_scale_factor = 0;
   int last_scale_update_iter = 0, n_log_scale_factor = 0, scale_updates = 0;
   long long admm_iters = 0;
-  double alg_bytes = 0;
   // iteration marks (bench.py)
   int mark_begin = -1, mark_end = -1;
   cudaEvent_t mark_ev[2] = {nullptr, nullptr};
@@ -829,7 +805,7 @@ static int populate_residuals(SCS_WORK *w, int iter) {
   c.launches += 2; c.spmv_calls += 2;
   CUDA_OK(cudaGetLastError());
   if (c.fetch_scalars()) return -1;
-  w->ev.flush();
+  w->ls.tot_cg_its = c.S_host->cg_its_total;
   const double *R = c.S_host->res;
   HostResid &r = w->r_n;
   r.last_iter = iter;
@@ -912,36 +888,155 @@ static int update_scale(SCS_WORK *w, int iter) {
   return 0;
 }
 
+// SURVEY.md 8(d) byte model, from the counters of the loop: ADMM iterations, CG iterations
+// (device counter), residual checks and AA applications since the workspace was created.
+static double model_bytes(const SCS_WORK *w, long long iters, long long cg_its, long long checks, long long aa_n) {
+  const LinSys &ls = w->ls;
+  const double n = w->n, m = w->m, l = w->l;
+  const double per_iter = 2.0 * (ls.bytes_A() + ls.bytes_At()) + ls.bytes_P() + 6.0 * (n + m) * 8.0 + 14.0 * l * 8.0;
+  const double per_cg = ls.bytes_A() + ls.bytes_At() + ls.bytes_P() + 10.0 * n * 8.0;
+  const double per_check = ls.bytes_A() + ls.bytes_At() + ls.bytes_P() + 20.0 * l * 8.0;
+  const double per_aa = w->has_aa ? (3.0 * w->aa.mem + 12.0) * l * 8.0 : 0.0;
+  return iters * per_iter + cg_its * per_cg + checks * per_check + aa_n * per_aa;
+}
+
+// total kernels of this library launched so far: host-counted launches + the CG-loop kernels
+// (4 per CG iteration that really executed; decided on the device)
+static long long total_launches(const SCS_WORK *w, long long cg_its) { return w->c.launches + 4 * cg_its; }
+
+static int set_kt(SCS_WORK *w, int on) {
+  Ctx &c = w->c;
+  static const unsigned long long zeros[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CUDA_OK(cudaMemcpyAsync(&c.S->kt_ticket[0], zeros, sizeof(unsigned int) * 4 + sizeof(unsigned long long) * 4,
+                          cudaMemcpyHostToDevice, c.stream));
+  CUDA_OK(cudaMemcpyAsync(&c.S->kt_on, &on, sizeof(int), cudaMemcpyHostToDevice, c.stream));
+  return 0;
+}
+
 static void mark_open(SCS_WORK *w, int iter) {
-  cudaEventRecord(w->mark_ev[0], w->c.stream);
-  w->mk_launch0 = w->c.launches;
-  w->mk_cg0 = w->ls.tot_cg_its;
-  w->mk_bytes0 = w->alg_bytes;
+  Ctx &c = w->c;
+  c.fetch_scalars();  // counters at the start of the region (synchronises)
+  w->mk_cg0 = c.S_host->cg_its_total;
+  w->mk_launch0 = total_launches(w, w->mk_cg0);
+  w->mk_bytes0 = model_bytes(w, w->admm_iters + iter, w->mk_cg0, w->n_checks, w->n_aa);
   w->mk_iter0 = iter;
   w->mk_open = true;
-  w->c.prof.used = 0;
-  for (int k = 0; k < 4; ++k) { w->c.prof.ms[k] = 0; w->c.prof.cnt[k] = 0; }
-  w->c.prof_enable(true);
+  set_kt(w, 1);
+  cudaEventRecord(w->mark_ev[0], c.stream);
 }
 static void mark_close(SCS_WORK *w, int iter) {
-  cudaEventRecord(w->mark_ev[1], w->c.stream);
-  cudaStreamSynchronize(w->c.stream);
-  w->c.prof_flush(0x7fffffff);
-  w->c.prof_enable(false);
+  Ctx &c = w->c;
+  cudaEventRecord(w->mark_ev[1], c.stream);
+  c.fetch_scalars();
   float ms = 0.f;
   cudaEventElapsedTime(&ms, w->mark_ev[0], w->mark_ev[1]);
+  const DevScalars *h = c.S_host;
   ScsB200Marks &mk = w->marks;
   mk.ms = ms;
   mk.iters = iter - w->mk_iter0;
-  mk.cg_iters = w->ls.tot_cg_its - w->mk_cg0;
-  mk.kernel_launches = w->c.launches - w->mk_launch0;
-  mk.algorithmic_bytes = w->alg_bytes - w->mk_bytes0;
-  mk.spmv_a_ms = w->c.prof.ms[0]; mk.spmv_g_ms = w->c.prof.ms[1];
-  mk.spmv_a_launches = w->c.prof.cnt[0]; mk.spmv_g_launches = w->c.prof.cnt[1];
+  mk.cg_iters = h->cg_its_total - w->mk_cg0;
+  mk.kernel_launches = total_launches(w, h->cg_its_total) - w->mk_launch0;
+  mk.algorithmic_bytes = model_bytes(w, w->admm_iters + iter, h->cg_its_total, w->n_checks, w->n_aa) - w->mk_bytes0;
+  mk.spmv_a_ms = h->kt_ns[0] * 1e-6; mk.spmv_g_ms = h->kt_ns[1] * 1e-6;
+  mk.spmv_a_launches = h->kt_cnt[0]; mk.spmv_g_launches = h->kt_cnt[1];
   mk.bytes_a = w->ls.bytes_A();
   mk.bytes_g = w->ls.bytes_At() + w->ls.bytes_P();
+  set_kt(w, 0);
   w->mk_open = false;
   w->mk_done = true;
+}
+
+// enqueue the front half of one ADMM iteration: k_prep .. cone projections (scs.c:1315-1340).
+// In graph mode `loop` carries the WHILE handle and the CG iterations are NOT enqueued here.
+static int enqueue_front_head(SCS_WORK *w, CgCtl loop) {
+  Ctx &c = w->c;
+  const int n = w->n, m = w->m, gl = ew_grid(c, w->l);
+  cudaStream_t st = c.stream;
+  if (w->has_aa)
+    k_prep<true><<<gl, kThreads, 0, st>>>(w->v, w->v_prev, w->u_t, w->u, w->g, w->diag_r, w->ws, n, m, c.red, c.S);
+  else
+    k_prep<false><<<gl, kThreads, 0, st>>>(w->v, w->v_prev, w->u_t, w->u, w->g, w->diag_r, w->ws, n, m, c.red, c.S);
+  c.launches++;
+  return w->ls.enqueue_head(w->u_t, w->ws, loop);
+}
+static int enqueue_front_tail(SCS_WORK *w) {
+  Ctx &c = w->c;
+  const int n = w->n, m = w->m, gl = ew_grid(c, w->l);
+  cudaStream_t st = c.stream;
+  if (w->ls.enqueue_tail(w->u_t)) return -1;
+  k_rootplus<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->u_t, w->v, w->g, w->diag_r, n + m, c.red, c.S);
+  k_pre<<<gl, kThreads, 0, st>>>(w->u_t, w->u, w->rsk, w->v, w->g, w->diag_r, n, m, w->cone.z, w->cone.z + w->cone.l, c.S);
+  c.launches += 2;
+  if (w->cone.has_nonlinear()) {
+    if (w->cone.project_nonlinear(w->u + n, w->rsk + n, w->diag_r + n)) return -1;
+  }
+  return 0;
+}
+
+// Capture the front half into a CUDA graph whose CG loop is a WHILE conditional node: one
+// graph launch per ADMM iteration, no host synchronisation until the next residual check.
+static int build_iter_graph(SCS_WORK *w) {
+  Ctx &c = w->c;
+  const char *env = getenv("SCS_B200_NO_GRAPH");
+  if (env && env[0] == '1') return 0;
+  cudaStream_t st = c.stream;
+  const long long l0 = c.launches, s0 = c.spmv_calls;
+  bool capturing = false, ok = false;
+  do {
+    if (cudaStreamCreateWithFlags(&w->st_body, cudaStreamNonBlocking) != cudaSuccess) break;
+    if (cudaGraphCreate(&w->graph, 0) != cudaSuccess) break;
+    CgCtl loop;
+    if (cudaGraphConditionalHandleCreate(&loop.h, w->graph, 0, cudaGraphCondAssignDefault) != cudaSuccess) break;
+    loop.use_h = 1;
+    if (cudaStreamBeginCaptureToGraph(st, w->graph, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess) break;
+    capturing = true;
+    if (enqueue_front_head(w, loop)) break;
+    // WHILE node after everything captured so far
+    cudaStreamCaptureStatus status;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t ndeps = 0;
+    if (cudaStreamGetCaptureInfo_v2(st, &status, nullptr, nullptr, &deps, &ndeps) != cudaSuccess) break;
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = loop.h;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t wnode;
+    if (cudaGraphAddNode(&wnode, w->graph, deps, ndeps, &np) != cudaSuccess) break;
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    if (cudaStreamUpdateCaptureDependencies(st, &wnode, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) break;
+    {  // loop body: one CG iteration, captured on a second stream into the body graph
+      if (cudaStreamBeginCaptureToGraph(w->st_body, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess) break;
+      c.stream = w->st_body;
+      const int rc = w->ls.enqueue_cg_iter(w->u_t, loop, -1);
+      c.stream = st;
+      cudaGraph_t tmp = nullptr;
+      if (cudaStreamEndCapture(w->st_body, &tmp) != cudaSuccess || rc) break;
+    }
+    if (enqueue_front_tail(w)) break;
+    cudaGraph_t tmp = nullptr;
+    capturing = false;
+    if (cudaStreamEndCapture(st, &tmp) != cudaSuccess) break;
+    if (cudaGraphInstantiate(&w->gexec, w->graph, 0) != cudaSuccess) break;
+    ok = true;
+  } while (0);
+  if (capturing) {
+    cudaGraph_t tmp = nullptr;
+    cudaStreamEndCapture(st, &tmp);
+  }
+  w->graph_launches = c.launches - l0;
+  w->graph_spmv = c.spmv_calls - s0;
+  c.launches = l0;
+  c.spmv_calls = s0;
+  if (!ok) {
+    cudaGetLastError();
+    B200_PRINTF("WARN: CUDA graph capture of the ADMM iteration failed; using stream launches.\n");
+    if (w->gexec) { cudaGraphExecDestroy(w->gexec); w->gexec = nullptr; }
+    if (w->graph) { cudaGraphDestroy(w->graph); w->graph = nullptr; }
+    return 0;
+  }
+  w->use_graph = true;
+  return 0;
 }
 
 static void free_work(SCS_WORK *w) {
@@ -953,7 +1048,9 @@ static void free_work(SCS_WORK *w) {
   w->ls.destroy();
   w->cone.destroy();
   if (w->has_aa) w->aa.destroy();
-  w->ev.destroy();
+  if (w->gexec) cudaGraphExecDestroy(w->gexec);
+  if (w->graph) cudaGraphDestroy(w->graph);
+  if (w->st_body) cudaStreamDestroy(w->st_body);
   dev_free(w->u); dev_free(w->u_t); dev_free(w->v); dev_free(w->v_prev); dev_free(w->rsk); dev_free(w->g);
   dev_free(w->diag_r); dev_free(w->b); dev_free(w->cvec); dev_free(w->D); dev_free(w->E); dev_free(w->ws);
   dev_free(w->sol_x); dev_free(w->sol_y); dev_free(w->sol_s);
@@ -1088,7 +1185,6 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
     if (w->c.init(current_device())) break;
     Ctx &c = w->c;
     cudaStream_t st = c.stream;
-    if (w->ev.init()) break;
     if (dev_alloc_zero(&w->u, (size_t)l, st) || dev_alloc_zero(&w->u_t, (size_t)l, st) ||
         dev_alloc_zero(&w->v, (size_t)l, st) || dev_alloc_zero(&w->v_prev, (size_t)l, st) ||
         dev_alloc_zero(&w->rsk, (size_t)l, st) || dev_alloc_zero(&w->g, (size_t)l, st) ||
@@ -1136,6 +1232,8 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
     }
     if (c.sync()) break;
     if (cudaGetLastError() != cudaSuccess) break;
+    if (build_iter_graph(w)) break;
+    if (c.sync()) break;
     ok = true;
   } while (0);
   if (!ok) {
@@ -1167,7 +1265,6 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   w->last_scale_update_iter = 0; w->sum_log_scale_factor = 0.; w->n_log_scale_factor = 0; w->scale_updates = 0;
   w->time_limit_reached = 0;
   w->r_n.last_iter = -1; w->r_o.last_iter = -1;
-  w->ev.reset();
   cudaMemsetAsync(&c.S->aa_rejected, 0, 2 * sizeof(int), st);  // safeguard counters of this solve
   if (warm_start) {
     if (!sol->x || !sol->y || !sol->s) {
@@ -1185,10 +1282,13 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   if (stgs->verbose) print_header();
 
   const int gl = ew_grid(c, l);
-  const int zl = w->cone.z + w->cone.l;
   const bool accel = w->has_aa;
   const int interval = stgs->acceleration_interval;
-  const double bytes_iter_fixed = 14.0 * l * 8.0;
+  {  // device-side loop state of this solve: iteration index and phase clocks
+    static const unsigned long long zeros[5] = {0, 0, 0, 0, 0};
+    cudaMemsetAsync(&c.S->iter, 0, sizeof(int), st);
+    cudaMemcpyAsync(&c.S->t_mark, zeros, sizeof(zeros), cudaMemcpyHostToDevice, st);
+  }
   int i;
   for (i = 0; i < stgs->max_iters; ++i) {
     if (w->mark_begin >= 0) {
@@ -1197,38 +1297,24 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
     }
     // ---- Anderson acceleration (scs.c:1306-1313)
     if (accel && i > 0 && i % interval == 0) {
-      const int sl = w->ev.begin(2, st);
+      k_stamp<<<1, 1, 0, st>>>(c.S, -1);
       if (w->aa.apply(w->v, w->v_prev, &c.S->vnorm2))
         return failure(w, m, n, sol, info, SCS_FAILED, "error in aa_apply", "failure");
-      w->ev.end(sl, st);
-      w->alg_bytes += (3.0 * w->aa.mem + 12.0) * l * 8.0;
+      k_stamp<<<1, 1, 0, st>>>(c.S, 2);
+      c.launches += 2;
+      w->n_aa++;
     }
-    // ---- linear system (scs.c:1326-1332)
-    const int sl_lin = w->ev.begin(0, st);
-    if (accel)
-      k_prep<true><<<gl, kThreads, 0, st>>>(w->v, w->v_prev, w->u_t, w->u, w->g, w->diag_r, w->ws, n, m, i, c.red, c.S);
-    else
-      k_prep<false><<<gl, kThreads, 0, st>>>(w->v, w->v_prev, w->u_t, w->u, w->g, w->diag_r, w->ws, n, m, i, c.red, c.S);
-    c.launches++;
-    if (w->ls.solve_dev(w->u_t, w->ws, 0))
-      return failure(w, m, n, sol, info, SCS_FAILED, "error in project_lin_sys", "failure");
-    k_rootplus<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->u_t, w->v, w->g, w->diag_r, n + m, i, c.red, c.S);
-    c.launches++;
-    w->ev.end(sl_lin, st);
-    {
-      const int K = w->ls.last_its;
-      w->alg_bytes += (K + 2.0) * (w->ls.bytes_A() + w->ls.bytes_At()) + (K + 1.0) * w->ls.bytes_P() +
-                      K * 10.0 * n * 8.0 + 6.0 * (n + m) * 8.0 + bytes_iter_fixed;
+    // ---- linear system + cones (scs.c:1326-1340): one graph launch, or the same kernels
+    //      enqueued on the stream with the CG loop driven from the host
+    if (w->use_graph) {
+      if (cudaGraphLaunch(w->gexec, st) != cudaSuccess)
+        return failure(w, m, n, sol, info, SCS_FAILED, "error launching the iteration graph", "failure");
+      c.launches += w->graph_launches;
+      c.spmv_calls += w->graph_spmv;
+    } else {
+      if (enqueue_front_head(w, CgCtl{}) || w->ls.solve_dev_loop(w->u_t, 0) || enqueue_front_tail(w))
+        return failure(w, m, n, sol, info, SCS_FAILED, "error in project_lin_sys / project_cones", "failure");
     }
-    // ---- cones (scs.c:1334-1340)
-    const int sl_cone = w->ev.begin(1, st);
-    k_pre<<<gl, kThreads, 0, st>>>(w->u_t, w->u, w->rsk, w->v, w->g, w->diag_r, n, m, w->cone.z, zl, i, c.S);
-    c.launches++;
-    if (w->cone.has_nonlinear()) {
-      if (w->cone.project_nonlinear(w->u + n, w->rsk + n, w->diag_r + n))
-        return failure(w, m, n, sol, info, SCS_FAILED, "error in project_cones", "failure");
-    }
-    w->ev.end(sl_cone, st);
 
     const bool check = (i % kConvergedInterval == 0);
     const bool print = stgs->verbose && (i % kPrintInterval == 0);
@@ -1237,7 +1323,7 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
       c.launches++;
       if (check && g_int_detected) return failure(w, m, n, sol, info, SCS_SIGINT, "interrupted", "interrupted");
       if (populate_residuals(w, i)) return failure(w, m, n, sol, info, SCS_FAILED, "error in residuals", "failure");
-      w->alg_bytes += w->ls.bytes_A() + w->ls.bytes_At() + w->ls.bytes_P() + 20.0 * l * 8.0;
+      w->n_checks++;
       if (check) {
         if ((info->status_val = has_converged(w)) != 0) break;
         if (stgs->time_limit_secs && ms_since(t0) > 1000. * stgs->time_limit_secs) {
@@ -1257,14 +1343,11 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
     }
     // ---- AA safeguard (scs.c:1386-1394); the aa_norm > 0 gate is evaluated on the device
     if (accel && i > 0 && i % interval == 0) {
-      const int sl = w->ev.begin(2, st);
+      k_stamp<<<1, 1, 0, st>>>(c.S, -1);
       if (w->aa.safeguard(w->v, w->v_prev, &c.S->vnorm2, &c.S->aa_rejected, &c.S->aa_accepted))
         return failure(w, m, n, sol, info, SCS_FAILED, "error in aa_safeguard", "failure");
-      w->ev.end(sl, st);
-    }
-    if (w->ev.used > EventAccum::kSlots - 8) {
-      if (c.sync()) return failure(w, m, n, sol, info, SCS_FAILED, "sync", "failure");
-      w->ev.flush();
+      k_stamp<<<1, 1, 0, st>>>(c.S, 2);
+      c.launches += 2;
     }
   }
   if (w->mk_open) mark_close(w, i);
@@ -1283,7 +1366,7 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   c.launches++;
   if (populate_residuals(w, i)) return failure(w, m, n, sol, info, SCS_FAILED, "error in residuals", "failure");
   if (c.fetch_scalars()) return failure(w, m, n, sol, info, SCS_FAILED, "fetch", "failure");
-  w->ev.flush();
+  w->ls.tot_cg_its = c.S_host->cg_its_total;
   const double nm_s = c.S_host->fin[0], nm_y = c.S_host->fin[1], sty = c.S_host->fin[2];
   const HostResid &r = w->r_o;
   info->setup_time = w->setup_time;
@@ -1347,11 +1430,10 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   if (d2h(c, sol->x, w->sol_x, (size_t)n) || d2h(c, sol->y, w->sol_y, (size_t)m) || d2h(c, sol->s, w->sol_s, (size_t)m) ||
       c.sync())
     return failure(w, m, n, sol, info, SCS_FAILED, "solution download", "failure");
-  w->ev.flush();
   info->solve_time = ms_since(t0);
-  info->lin_sys_time = w->ev.total[0];
-  info->cone_time = w->ev.total[1];
-  info->accel_time = w->ev.total[2];
+  info->lin_sys_time = c.S_host->phase_ns[0] * 1e-6;  // %globaltimer phase clocks, see phase_lap()
+  info->cone_time = c.S_host->phase_ns[1] * 1e-6;
+  info->accel_time = c.S_host->phase_ns[2] * 1e-6;
   if (stgs->verbose) print_footer(info);
   end_interrupt_listener();
   return info->status_val;
@@ -1375,12 +1457,12 @@ extern "C" scs_int scs(const ScsData *d, const ScsCone *k, const ScsSettings *st
 // ------------------------------------------------------------------ measurement -------
 extern "C" scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out) {
   if (!w || !out) return -1;
-  out->kernel_launches = w->c.launches;
+  out->kernel_launches = total_launches(w, w->ls.tot_cg_its);
   out->cg_iters = w->ls.tot_cg_its;
   out->admm_iters = w->admm_iters;
   out->spmv_calls = w->c.spmv_calls;
   out->spmv_ms = 0.0;
-  out->algorithmic_bytes = w->alg_bytes;
+  out->algorithmic_bytes = model_bytes(w, w->admm_iters, w->ls.tot_cg_its, w->n_checks, w->n_aa);
   out->h2d_bytes = w->c.h2d;
   out->d2h_bytes = w->c.d2h;
   return 0;

@@ -161,11 +161,11 @@ int chunks_build(Ctx &c, ChunkList &out, const CsrDev &a, const CsrDev *b) {
     CUDA_OK(cudaMemcpyAsync(pb.data(), b->ptr, sizeof(int) * pb.size(), cudaMemcpyDeviceToHost, c.stream));
   }
   CUDA_OK(cudaStreamSynchronize(c.stream));
-  std::vector<Chunk> ch;
+  std::vector<int4> ch;
   build_chunks_host(a.nrows, pa.data(), b ? pb.data() : nullptr, ch);
   out.n = (int)ch.size();
   if (dev_alloc(&out.d, ch.size())) return -1;
-  CUDA_OK(cudaMemcpyAsync(out.d, ch.data(), sizeof(Chunk) * ch.size(), cudaMemcpyHostToDevice, c.stream));
+  CUDA_OK(cudaMemcpyAsync(out.d, ch.data(), sizeof(int4) * ch.size(), cudaMemcpyHostToDevice, c.stream));
   CUDA_OK(cudaStreamSynchronize(c.stream));
   out.grid = out.n < c.grid_ew() ? (out.n > 0 ? out.n : 1) : c.grid_ew();
   return 0;

@@ -28,33 +28,20 @@ struct CsrDev {
   double *val = nullptr;  // nnz
 };
 
-// One unit of work of the row engine: rows [row_begin, row_end) whose non-zeros (of A, and of
-// B for the fused two-matrix kernels) fit one shared-memory tile.  The nnz offsets are kept in
-// the descriptor so the coalesced val/idx streams can be issued straight after the
-// descriptor load, without first chasing the row pointers.
-struct __align__(16) Chunk {
-  int row_begin, row_end;
-  int lg;      // log2(lanes per row) for the tile reduction (0..5), or kLongRow
-  int pad;
-  int a0, na;  // first non-zero / count inside A for these rows
-  int b0, nb;  // same for B (0, 0 when the list was built for one matrix)
-};
-constexpr int kLongRow = 8;     // Chunk::lg marker: a single row longer than a tile
-constexpr int kTile = 2048;     // non-zeros staged per chunk (16 KB of FP64 products)
-constexpr int kIpt = kTile / kThreads;
-constexpr int kMaxRows = 1024;  // rows per chunk
-
+// row_begin, row_end, log2(lanes per row) (8 == whole CTA), unused
 struct ChunkList {
   int n = 0;
-  Chunk *d = nullptr;
+  int4 *d = nullptr;
   int grid = 1;
 };
 
 // Build the chunk list on the host from one or two row-pointer arrays (second may be null;
-// used to fuse P's rows with A' rows).  Greedy: a chunk is closed when the next row would
-// overflow the tile, when it holds kMaxRows rows, or when the row-length class drifts by
-// more than 2x (so one lanes-per-row setting fits all its rows).
-inline void build_chunks_host(int nrows, const int *ptr1, const int *ptr2, std::vector<Chunk> &out) {
+// used to fuse P's rows with A' rows).  Greedy: close a chunk when it holds >= target nnz,
+// >= max_rows rows, or the row-length class changes by more than 2x.
+inline void build_chunks_host(int nrows, const int *ptr1, const int *ptr2, std::vector<int4> &out) {
+  const long long target = 4096;
+  const int max_rows = 2048;
+  const long long long_row = 16384;
   out.clear();
   int r = 0;
   auto rowlen = [&](int i) -> long long {
@@ -67,194 +54,138 @@ inline void build_chunks_host(int nrows, const int *ptr1, const int *ptr2, std::
     while ((1ll << (c + 1)) <= L) ++c;
     return c;  // floor(log2(max(L,1)))
   };
-  auto emit = [&](int begin, int end, int lg) {
-    Chunk ch;
-    ch.row_begin = begin; ch.row_end = end; ch.lg = lg; ch.pad = 0;
-    ch.a0 = ptr1[begin]; ch.na = ptr1[end] - ptr1[begin];
-    ch.b0 = ptr2 ? ptr2[begin] : 0; ch.nb = ptr2 ? ptr2[end] - ptr2[begin] : 0;
-    out.push_back(ch);
-  };
   while (r < nrows) {
-    const long long L0 = rowlen(r);
-    if (L0 > kTile) {  // very long row: whole CTA loops over it
-      emit(r, r + 1, kLongRow);
+    long long L0 = rowlen(r);
+    if (L0 >= long_row) {  // very long row: whole CTA
+      out.push_back(make_int4(r, r + 1, 8, 0));
       ++r;
       continue;
     }
-    const int begin = r;
+    int begin = r;
     long long nnz = 0;
-    const int c0 = cls(L0 > 0 ? L0 : 1);
+    int c0 = cls(L0 > 0 ? L0 : 1);
     int cmin = c0, cmax = c0;
-    while (r < nrows && r - begin < kMaxRows) {
-      const long long L = rowlen(r);
-      if (nnz + L > kTile) break;
-      const int c = cls(L > 0 ? L : 1);
-      const int nmin = c < cmin ? c : cmin, nmax = c > cmax ? c : cmax;
+    while (r < nrows) {
+      long long L = rowlen(r);
+      if (L >= long_row) break;
+      int c = cls(L > 0 ? L : 1);
+      int nmin = c < cmin ? c : cmin, nmax = c > cmax ? c : cmax;
       if (r > begin && (nmax - nmin > 1) && (r - begin) >= 32) break;
       cmin = nmin; cmax = nmax;
       nnz += L;
       ++r;
+      if (nnz >= target || r - begin >= max_rows) break;
     }
-    const int rows = r - begin;
-    const long long avg = rows > 0 ? (nnz + rows - 1) / rows : 1;
+    int rows = r - begin;
+    long long avg = rows > 0 ? (nnz + rows - 1) / rows : 1;
     int lg = 0;
     while ((2ll << lg) <= avg && lg < 5) ++lg;  // lanes = pow2_floor(avg) capped at 32
-    emit(begin, r, lg);
+    out.push_back(make_int4(begin, r, lg, 0));
   }
 }
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------
-// element functors: the value one stored entry contributes (map) and how contributions of
-// one row combine (comb); init() is comb's neutral element
+// element functors: how one stored entry contributes to its row's accumulator
 // ---------------------------------------------------------------------------------------
-struct ElemMul {  // sum_k val * x[col]              (SpMV)
+struct ElemMul {  // acc += val * x[col]            (SpMV)
   const double *__restrict__ x;
   __device__ __forceinline__ double init() const { return 0.0; }
-  __device__ __forceinline__ double map(double v, int c) const { return v * __ldg(x + c); }
+  __device__ __forceinline__ double term(double a, double v, int c) const { return fma(v, __ldg(x + c), a); }
   __device__ __forceinline__ double comb(double a, double b) const { return a + b; }
 };
-struct ElemAbsMax {  // max_k |val|                  (Ruiz row/col norms, scs_matrix.c:224-228,267-273)
+struct ElemAbsMax {  // acc = max(acc, |val|)       (Ruiz row/col norms, scs_matrix.c:224-228,267-273)
   __device__ __forceinline__ double init() const { return 0.0; }
-  __device__ __forceinline__ double map(double v, int) const { return fabs(v); }
+  __device__ __forceinline__ double term(double a, double v, int) const { return fmax(a, fabs(v)); }
   __device__ __forceinline__ double comb(double a, double b) const { return fmax(a, b); }
 };
-struct ElemSumSq {  // sum_k val^2                   (L2 pass, scs_matrix.c:293-297,337-339)
+struct ElemSumSq {  // acc += val^2                 (L2 pass, scs_matrix.c:293-297,337-339)
   __device__ __forceinline__ double init() const { return 0.0; }
-  __device__ __forceinline__ double map(double v, int) const { return v * v; }
+  __device__ __forceinline__ double term(double a, double v, int) const { return fma(v, v, a); }
   __device__ __forceinline__ double comb(double a, double b) const { return a + b; }
 };
-struct ElemSqDiv {  // sum_k val^2 / d[col]          (preconditioner, cpu/indirect/private.c:65-68)
+struct ElemSqDiv {  // acc += val^2 / d[col]        (preconditioner, cpu/indirect/private.c:65-68)
   const double *__restrict__ d;
   __device__ __forceinline__ double init() const { return 0.0; }
-  __device__ __forceinline__ double map(double v, int c) const { return v * v / __ldg(d + c); }
+  __device__ __forceinline__ double term(double a, double v, int c) const { return a + v * v / __ldg(d + c); }
   __device__ __forceinline__ double comb(double a, double b) const { return a + b; }
 };
 
-// Stage the mapped entries [k0, k0+cnt) of M into the shared tile: every load of the
-// (val, idx) streams is independent and coalesced, kIpt of each in flight per thread.
 template <class Elem>
-__device__ __forceinline__ void stage_tile(const CsrDev &M, const Elem &e, int k0, int cnt, double *tile) {
-  const double *__restrict__ val = M.val + k0;
-  const int *__restrict__ idx = M.idx + k0;
-  double v[kIpt];
-  int c[kIpt];
-#pragma unroll
-  for (int i = 0; i < kIpt; ++i) {
-    const int k = threadIdx.x + i * kThreads;
-    if (k < cnt) {
-      v[i] = __ldcs(val + k);
-      c[i] = __ldcs(idx + k);
-    }
+__device__ __forceinline__ double row_partial(const CsrDev &M, const Elem &e, int row, int lane, int G,
+                                              double acc) {
+  const int start = M.ptr[row], end = M.ptr[row + 1];
+  int k = start + lane;
+  // two independent loads in flight per lane
+  for (; k + G < end; k += 2 * G) {
+    const double v0 = __ldcs(M.val + k), v1 = __ldcs(M.val + k + G);
+    const int c0 = __ldcs(M.idx + k), c1 = __ldcs(M.idx + k + G);
+    acc = e.term(acc, v0, c0);
+    acc = e.term(acc, v1, c1);
   }
-#pragma unroll
-  for (int i = 0; i < kIpt; ++i) {
-    const int k = threadIdx.x + i * kThreads;
-    if (k < cnt) tile[k] = e.map(v[i], c[i]);
-  }
+  if (k < end) acc = e.term(acc, __ldcs(M.val + k), __ldcs(M.idx + k));
+  return acc;
 }
 
-// whole-CTA reduction of one long row; result valid in thread 0
-template <class Elem>
-__device__ __forceinline__ double long_row(const CsrDev &M, const Elem &e, int k0, int cnt, double *sh8) {
-  double acc = e.init();
-  for (int k = threadIdx.x; k < cnt; k += kThreads) acc = e.comb(acc, e.map(__ldcs(M.val + k0 + k), __ldcs(M.idx + k0 + k)));
-  for (int o = 16; o > 0; o >>= 1) acc = e.comb(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sh8[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  double t = sh8[0];
-  for (int w = 1; w < kThreads / 32; ++w) t = e.comb(t, sh8[w]);
-  return t;
-}
-
-// Generic row engine ("CSR-stream").  For every row r: acc = reduce_k Elem(A[r,k]) (and the
-// same over B's row r with Elem2 when DUAL), then epi.row(st, r, acc) -- or
-// epi.row2(st, r, accA, accB) when Epi::kSeparate -- with consecutive threads on
-// consecutive rows.  After the sweep every thread calls epi.finish(st, ws, S) (grid
-// reduction / scalar finalisation).  A persistent grid walks the chunk list round-robin.
+// Generic row engine.  For every row r: acc = reduce_k Elem(A[r,k]) (+ reduce over B's
+// row r with Elem2 when DUAL), then epi.row(st, r, acc) on one lane.  After the sweep every
+// thread calls epi.finish(st, ws, S) (grid reduction / scalar finalisation).
 // skip: optional device flag; when set the kernel exits at once (CG already converged).
 template <class Elem, class Elem2, class Epi, bool DUAL>
-__global__ void __launch_bounds__(kThreads, 4)
-row_kernel(CsrDev A, Elem ea, CsrDev B, Elem2 eb, const Chunk *__restrict__ chunks, int nchunks, Epi epi,
+__global__ void __launch_bounds__(kThreads)
+row_kernel(CsrDev A, Elem ea, CsrDev B, Elem2 eb, const int4 *__restrict__ chunks, int nchunks, Epi epi,
            RedWs ws, DevScalars *S, const int *skip) {
   if (skip != nullptr && *skip != 0) return;
-  constexpr bool SEP = DUAL && Epi::kSeparate;
-  __shared__ double tile[kTile];
-  __shared__ int sptr[(DUAL ? 2 : 1) * (kMaxRows + 1)];
-  __shared__ double racc[(SEP ? 2 : 1) * kMaxRows];
-  __shared__ double sh8[kThreads / 32];
+  __shared__ double shrow[32];
   typename Epi::State st;
   epi.init(st);
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    const int4 c0 = __ldg(reinterpret_cast<const int4 *>(chunks + c));
-    const int4 c1 = __ldg(reinterpret_cast<const int4 *>(chunks + c) + 1);
-    const int r0 = c0.x, nrows = c0.y - c0.x, lg = c0.z;
-    const int a0 = c1.x, na = c1.y, b0 = c1.z, nb = c1.w;
-    if (lg == kLongRow) {
-      double t = long_row(A, ea, a0, na, sh8);
-      double t2 = eb.init();
-      if (DUAL) t2 = long_row(B, eb, b0, nb, sh8);
-      if (threadIdx.x == 0) {
-        if (SEP) epi.row2(st, r0, t, t2);
-        else epi.row(st, r0, DUAL ? ea.comb(t, t2) : t);
-      }
-      continue;
-    }
-    // ---- phase 1: stream the chunk's entries, gather, stage products; row pointers too
-    for (int i = threadIdx.x; i <= nrows; i += kThreads) {
-      sptr[i] = __ldg(A.ptr + r0 + i) - a0;
-      if (DUAL) sptr[kMaxRows + 1 + i] = __ldg(B.ptr + r0 + i) - b0 + na;
-    }
-    stage_tile(A, ea, a0, na, tile);
-    if (DUAL) stage_tile(B, eb, b0, nb, tile + na);
-    __syncthreads();
-    // ---- phase 2: segmented reduction, G lanes per row
-    if (lg == 0) {
-      for (int i = threadIdx.x; i < nrows; i += kThreads) {
-        double acc = ea.init();
-        for (int k = sptr[i]; k < sptr[i + 1]; ++k) acc = ea.comb(acc, tile[k]);
-        if (DUAL) {
-          double acc2 = eb.init();
-          for (int k = sptr[kMaxRows + 1 + i]; k < sptr[kMaxRows + 2 + i]; ++k) acc2 = eb.comb(acc2, tile[k]);
-          if (SEP) epi.row2(st, r0 + i, acc, acc2);
-          else epi.row(st, r0 + i, ea.comb(acc, acc2));
-        } else {
-          epi.row(st, r0 + i, acc);
-        }
-      }
-    } else {
-      const int G = 1 << lg;
+    const int4 ch = chunks[c];
+    if (ch.z <= 5) {
+      const int G = 1 << ch.z;
       const int lane = threadIdx.x & (G - 1);
-      const int grp = threadIdx.x >> lg;
-      const int ngrp = kThreads >> lg;
-      for (int base = 0; base < nrows; base += ngrp) {
-        const int i = base + grp;
-        const bool valid = i < nrows;
+      const int grp = threadIdx.x >> ch.z;
+      const int ngrp = kThreads >> ch.z;
+      for (int base = ch.x; base < ch.y; base += ngrp) {
+        const int row = base + grp;
+        const bool valid = row < ch.y;
         double acc = ea.init(), acc2 = eb.init();
         if (valid) {
-          for (int k = sptr[i] + lane; k < sptr[i + 1]; k += G) acc = ea.comb(acc, tile[k]);
-          if (DUAL)
-            for (int k = sptr[kMaxRows + 1 + i] + lane; k < sptr[kMaxRows + 2 + i]; k += G) acc2 = eb.comb(acc2, tile[k]);
+          acc = row_partial(A, ea, row, lane, G, acc);
+          if (DUAL) acc2 = row_partial(B, eb, row, lane, G, acc2);
         }
-        if (DUAL && !SEP) acc = ea.comb(acc, acc2);
-        for (int o = G >> 1; o > 0; o >>= 1) {
-          acc = ea.comb(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-          if (SEP) acc2 = eb.comb(acc2, __shfl_xor_sync(0xffffffffu, acc2, o));
-        }
-        if (valid && lane == 0) {
-          racc[i] = acc;
-          if (SEP) racc[kMaxRows + i] = acc2;
+        if (DUAL && Epi::kSeparate) {
+          for (int o = G >> 1; o > 0; o >>= 1) {
+            acc = ea.comb(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+            acc2 = eb.comb(acc2, __shfl_xor_sync(0xffffffffu, acc2, o));
+          }
+          if (valid && lane == 0) epi.row2(st, row, acc, acc2);
+        } else {
+          if (DUAL) acc = ea.comb(acc, acc2);
+          for (int o = G >> 1; o > 0; o >>= 1) acc = ea.comb(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+          if (valid && lane == 0) epi.row(st, row, acc);
         }
       }
-      __syncthreads();
-      // ---- phase 3: epilogue, consecutive threads on consecutive rows
-      for (int i = threadIdx.x; i < nrows; i += kThreads) {
-        if (SEP) epi.row2(st, r0 + i, racc[i], racc[kMaxRows + i]);
-        else epi.row(st, r0 + i, racc[i]);
+    } else {  // whole CTA per row
+      for (int row = ch.x; row < ch.y; ++row) {
+        double acc = row_partial(A, ea, row, threadIdx.x, kThreads, ea.init());
+        double acc2 = eb.init();
+        if (DUAL) acc2 = row_partial(B, eb, row, threadIdx.x, kThreads, acc2);
+        for (int o = 16; o > 0; o >>= 1) {
+          acc = ea.comb(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+          acc2 = eb.comb(acc2, __shfl_xor_sync(0xffffffffu, acc2, o));
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { shrow[threadIdx.x >> 5] = acc; shrow[8 + (threadIdx.x >> 5)] = acc2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double t = shrow[0], t2 = shrow[8];
+          for (int w = 1; w < kThreads / 32; ++w) { t = ea.comb(t, shrow[w]); t2 = eb.comb(t2, shrow[8 + w]); }
+          if (DUAL && Epi::kSeparate) epi.row2(st, row, t, t2);
+          else epi.row(st, row, DUAL ? ea.comb(t, t2) : t);
+        }
       }
     }
-    __syncthreads();  // tile / sptr / racc are reused by the next chunk
   }
   epi.finish(st, ws, S);
 }
@@ -262,15 +193,15 @@ row_kernel(CsrDev A, Elem ea, CsrDev B, Elem2 eb, const Chunk *__restrict__ chun
 // Row map: val[k] = f(row, col, val[k]) -- used by the equilibration rescale.
 template <class F>
 __global__ void __launch_bounds__(kThreads)
-row_map_kernel(CsrDev A, const Chunk *__restrict__ chunks, int nchunks, F f) {
+row_map_kernel(CsrDev A, const int4 *__restrict__ chunks, int nchunks, F f) {
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    const Chunk ch = chunks[c];
-    const int lg = ch.lg <= 5 ? ch.lg : 8;
+    const int4 ch = chunks[c];
+    const int lg = ch.z <= 5 ? ch.z : 8;
     const int G = 1 << lg;
     const int lane = threadIdx.x & (G - 1);
     const int grp = threadIdx.x >> lg;
     const int ngrp = kThreads >> lg;
-    for (int row = ch.row_begin + grp; row < ch.row_end; row += ngrp) {
+    for (int row = ch.x + grp; row < ch.y; row += ngrp) {
       const int start = A.ptr[row], end = A.ptr[row + 1];
       for (int k = start + lane; k < end; k += G) A.val[k] = f(row, A.idx[k], A.val[k]);
     }

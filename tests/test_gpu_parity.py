@@ -407,6 +407,23 @@ def test_iteration_marks(scsb):
     assert mk["spmv_a_launches"] == mk["cg_iters"] + 50      # + the warm-start A s product of every ADMM iteration
 
 
+def test_graph_and_stream_paths_agree(scsb, monkeypatch):
+    """The graph-launched iteration (CG loop = WHILE node, no host sync between residual checks)
+    and the stream-launched one run the same kernels in the same order: identical results."""
+    K = dict(z=3, l=10, q=[4, 6], s=[3], ep=2, p=[0.4])
+    data, _ = problems.gen_feasible(K, 30, 0.3, seed=11, with_P=True)
+    kw = dict(eps_abs=1e-8, eps_rel=1e-8, max_iters=20000, verbose=False)
+    a = scsb.SCS(data, K, **kw).solve()
+    monkeypatch.setenv("SCS_B200_NO_GRAPH", "1")
+    b = scsb.SCS(data, K, **kw).solve()
+    monkeypatch.delenv("SCS_B200_NO_GRAPH")
+    assert a["info"]["status_val"] == b["info"]["status_val"] == 1
+    assert a["info"]["iter"] == b["info"]["iter"]
+    assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["y"], b["y"]) and np.array_equal(a["s"], b["s"])
+    for k in ("lin_sys_time", "cone_time", "accel_time"):
+        assert a["info"][k] > 0 and b["info"][k] > 0
+
+
 # ---------------------------------------------------------------- the live compiled reference --
 def test_against_live_reference(scsb, ref_scs):
     scs = ref_scs

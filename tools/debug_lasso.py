@@ -6,6 +6,7 @@ scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 n0 = int(1_000_000 * scale)
 data, cone, aux = problems.lasso(n0, 2 * n0, 100, 0)
-s = scsb.SCS(data, cone, verbose=True, max_iters=iters)
+eps_infeas = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-7
+s = scsb.SCS(data, cone, verbose=True, max_iters=iters, eps_infeas=eps_infeas)
 sol = s.solve(warm_start=False)
 print({k: v for k, v in sol["info"].items() if k != "aa_stats"})
