@@ -196,6 +196,11 @@ scs_int scs_b200_proj_dual_cone(scs_float *x, ScsB200ConeWork *c, const scs_floa
                                 const scs_float *r_y);
 /* SCS(finish_cone), cones.c:284-338 */
 void scs_b200_finish_cone(ScsB200ConeWork *c);
+/* Measurement hook (no reference counterpart): `reps` device-resident projections of the
+ * slowly drifting input x_r = x0 + r*step*x1 (r_y = 1); returns mean ms per projection (CUDA
+ * events on the workspace stream); *sweeps_out = mean Jacobi sweeps per PSD cone. */
+double scs_b200_bench_proj_cone(ScsB200ConeWork *c, const scs_float *x0, const scs_float *x1,
+                                scs_float step, scs_int reps, scs_int warmup, double *sweeps_out);
 
 /* SCS(accum_by_a / accum_by_atrans / accum_by_p), scs_matrix.c:135-199: y += A x etc.
  * A is CSC; P upper-triangular CSC.  Host buffers. Returns 0 on success. */

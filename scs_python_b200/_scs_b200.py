@@ -119,6 +119,8 @@ lib.scs_b200_lin_sys_cg_its.restype = c_int
 lib.scs_b200_lin_sys_cg_its.argtypes = [C.c_void_p]
 lib.scs_b200_init_cone.restype = C.c_void_p
 lib.scs_b200_init_cone.argtypes = [C.POINTER(ScsCone), c_int]
+lib.scs_b200_bench_proj_cone.restype = c_double
+lib.scs_b200_bench_proj_cone.argtypes = [C.c_void_p, p_double, p_double, c_double, c_int, c_int, p_double]
 lib.scs_b200_proj_dual_cone.restype = c_int
 lib.scs_b200_proj_dual_cone.argtypes = [p_double, C.c_void_p, p_double, p_double]
 lib.scs_b200_finish_cone.restype = None

@@ -18,9 +18,17 @@ struct PsdEntry {
   int s;          // matrix dimension as given (s or cs)
   int d;          // working dimension of the real symmetric problem (s, or 2*cs)
   int is_complex;
-  long long woff; // offset (in doubles) of this cone's d*d blocks inside G and V
+  long long woff; // offset (in doubles) of this cone's d*d blocks inside W, G and V
   int loff;       // offset into the eigenvalue scratch
   int pad;
+};
+// per-cone state of the warm-started eigen-solver (device)
+struct PsdState {
+  int age;        // projections since the eigenvector basis was last rebuilt from the identity
+  int cold;       // this projection starts from V = I (set by the prep kernel)
+  int sweeps;     // Jacobi sweeps of the last projection (diagnostic)
+  int pad;
+  double sigma;   // spectral shift: W = mat(x) + sigma I is PSD
 };
 
 struct ConeDev {
@@ -38,7 +46,11 @@ struct ConeDev {
   int n_q_small = 0, n_q_large = 0;
   PsdEntry *psd = nullptr;
   int n_psd = 0, psd_max_d = 0;
-  double *psd_G = nullptr, *psd_V = nullptr, *psd_lam = nullptr;
+  int n_psd_small = 0;  // entries [0, n_psd_small): one CTA each; the rest: one 4-CTA cluster each
+  double *psd_W = nullptr, *psd_G = nullptr, *psd_V = nullptr, *psd_lam = nullptr;
+  PsdState *psd_state = nullptr;
+  int psd_tiles = 0;    // ceil(psd_max_d / 64)
+  int psd_small_max_d = 0, psd_large_max_d = 0;
   double *d_bu = nullptr, *d_bl = nullptr, *box_t = nullptr;
   double *d_p = nullptr;
   int *bnd_off = nullptr, *bnd_len = nullptr;  // cones of size > 1 for enforce_cone_boundaries
