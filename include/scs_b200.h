@@ -238,6 +238,8 @@ typedef struct {
   double algorithmic_bytes;   /* SURVEY.md 8(d) byte model, accumulated per iteration */
   long long h2d_bytes;        /* bytes copied host->device by this workspace */
   long long d2h_bytes;        /* bytes copied device->host by this workspace */
+  long long collectives;      /* NCCL all-reduces issued (row-partitioned mode) */
+  long long collective_bytes; /* bytes all-reduced */
 } ScsB200Stats;
 scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out);
 
@@ -262,6 +264,21 @@ typedef struct {
   double bytes_a, bytes_g;   /* algorithmic bytes of ONE launch of each kernel */
 } ScsB200Marks;
 scs_int scs_b200_get_marks(const ScsWork *w, ScsB200Marks *out);
+
+/* Row-partitioned single problem over the GPUs of one box (no reference counterpart).
+ * One process per GPU.  Rank 0 obtains an id with scs_b200_dist_unique_id (128 bytes), every
+ * rank calls scs_b200_dist_init(rank, world, id) after scs_b200_set_device and before
+ * scs_init.  Workspaces created afterwards take the FULL problem on every rank, keep a
+ * cone-aligned block of rows of A, and return the full (x, y, s).  Collectives: NCCL sum
+ * all-reduces of n-vectors (A_g' z_g, once per CG iteration) and of a few reduction scalars. */
+scs_int scs_b200_dist_unique_id(void *out128);
+scs_int scs_b200_dist_init(scs_int rank, scs_int world, const void *id128);
+void scs_b200_dist_finalize(void);
+/* host-only: the block rank `rank` of `world` would own: out = {row0, m_local, nnz_local, z, l,
+ * bsize, qsize, ssize, cssize, ep, ed, psize} */
+scs_int scs_b200_dist_partition(const ScsData *d, const ScsCone *k, scs_int rank, scs_int world, scs_int out[12]);
+scs_int scs_b200_dist_rank(void);
+scs_int scs_b200_dist_world(void);
 
 /* Solve `count` independent problems on the current device, one after another on
  * `streams` concurrent streams (batch sharding across GPUs is done by the caller: one

@@ -124,6 +124,30 @@ class SCS(object):
         self._solver.update(b, c)
 
 
+def dist_init(rank=None, world=None):
+    """Row-partitioned mode (one process per GPU, e.g. under torchrun): call once per process
+    after selecting the GPU.  The NCCL id is shipped with torch.distributed when it is
+    initialised (any backend), which is plumbing only -- the data path is NCCL inside
+    libscsb200.so."""
+    import os
+    mod = _load_b200()
+    rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else int(world)
+    if world == 1:
+        mod.dist_init(0, 1, b"")
+        return
+    import torch.distributed as td
+    if not td.is_initialized():
+        raise RuntimeError("dist_init: initialise torch.distributed first (it only carries the 128-byte NCCL id)")
+    box = [mod.dist_unique_id() if rank == 0 else None]
+    td.broadcast_object_list(box, src=0)
+    mod.dist_init(rank, world, box[0])
+
+
+def dist_finalize():
+    _load_b200().dist_finalize()
+
+
 def solve(data, cone, **settings):
     """Legacy one-shot API (scs/py/__init__.py:217-230)."""
     solver = SCS(data, cone, **settings)

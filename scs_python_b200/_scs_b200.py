@@ -84,7 +84,8 @@ class ScsInfo(C.Structure):
 class ScsB200Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_longlong), ("cg_iters", C.c_longlong), ("admm_iters", C.c_longlong),
                 ("spmv_calls", C.c_longlong), ("spmv_ms", c_double), ("algorithmic_bytes", c_double),
-                ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong)]
+                ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
+                ("collectives", C.c_longlong), ("collective_bytes", C.c_longlong)]
 
 
 class ScsB200Marks(C.Structure):
@@ -115,6 +116,15 @@ lib.scs_solve_lin_sys.restype = c_int
 lib.scs_solve_lin_sys.argtypes = [C.c_void_p, p_double, p_double, c_double]
 lib.scs_update_lin_sys_diag_r.restype = c_int
 lib.scs_update_lin_sys_diag_r.argtypes = [C.c_void_p, p_double]
+lib.scs_b200_dist_unique_id.restype = c_int
+lib.scs_b200_dist_unique_id.argtypes = [C.c_void_p]
+lib.scs_b200_dist_init.restype = c_int
+lib.scs_b200_dist_init.argtypes = [c_int, c_int, C.c_void_p]
+lib.scs_b200_dist_finalize.restype = None
+lib.scs_b200_dist_rank.restype = c_int
+lib.scs_b200_dist_world.restype = c_int
+lib.scs_b200_dist_partition.restype = c_int
+lib.scs_b200_dist_partition.argtypes = [C.POINTER(ScsData), C.POINTER(ScsCone), c_int, c_int, C.POINTER(c_int * 12)]
 lib.scs_b200_lin_sys_cg_its.restype = c_int
 lib.scs_b200_lin_sys_cg_its.argtypes = [C.c_void_p]
 lib.scs_b200_init_cone.restype = C.c_void_p
@@ -151,6 +161,42 @@ lib.scs_b200_get_marks.restype = c_int
 lib.scs_b200_get_marks.argtypes = [C.c_void_p, C.POINTER(ScsB200Marks)]
 lib.scs_b200_bench_spmv.restype = c_double
 lib.scs_b200_bench_spmv.argtypes = [C.c_void_p, c_int, c_int, p_double]
+
+
+def dist_unique_id():
+    """128-byte NCCL id (rank 0 calls this and ships the bytes to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    if lib.scs_b200_dist_unique_id(buf) != 0:
+        raise RuntimeError("scs_b200_dist_unique_id failed (is libnccl.so.2 loadable?)")
+    return buf.raw
+
+
+def dist_init(rank, world, unique_id):
+    """Join the row-partitioned communicator: workspaces created afterwards keep a cone-aligned
+    block of rows of A on this rank's GPU (include/scs_b200.h)."""
+    buf = C.create_string_buffer(bytes(unique_id), 128) if world > 1 else None
+    if lib.scs_b200_dist_init(int(rank), int(world), buf) != 0:
+        raise RuntimeError("scs_b200_dist_init failed")
+
+
+def dist_finalize():
+    lib.scs_b200_dist_finalize()
+
+
+def dist_partition(shape, Ax, Ai, Ap, b, c, cone, rank, world):
+    """Host-only: what block `rank` of `world` would own (row0, m, nnz, z, l, bsize, qsize, ssize,
+    cssize, ep, ed, psize)."""
+    m, n = int(shape[0]), int(shape[1])
+    Ax = _check_float_1d(Ax, "Ax"); Ai = _check_int_1d(Ai, "Ai"); Ap = _check_int_1d(Ap, "Ap")
+    b = _check_float_1d(b, "b"); c = _check_float_1d(c, "c")
+    A = make_matrix(Ax, Ai, Ap, m, n)
+    k, keep = make_cone(cone)
+    d = ScsData(m, n, C.pointer(A), None, _dptr(b), _dptr(c))
+    out = (c_int * 12)()
+    if lib.scs_b200_dist_partition(C.byref(d), C.byref(k), int(rank), int(world), C.byref(out)) != 0:
+        raise ValueError("partition failed")
+    keys = ("row0", "m", "nnz", "z", "l", "bsize", "qsize", "ssize", "cssize", "ep", "ed", "psize")
+    return dict(zip(keys, list(out)))
 
 
 def version():

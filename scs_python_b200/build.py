@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libscsb200.so")
-SOURCES = ["sparse.cu", "linsys.cu", "cones.cu", "aa.cu", "scs_solver.cu"]
+SOURCES = ["sparse.cu", "linsys.cu", "cones.cu", "aa.cu", "dist.cu", "scs_solver.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=default", "--expt-relaxed-constexpr"]
 
@@ -67,7 +67,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         if verbose and err.strip():
             sys.stderr.write(err)
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xlinker", "-Bsymbolic", "-lcudart"]
+           "-Xlinker", "-Bsymbolic", "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

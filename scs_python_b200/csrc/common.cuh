@@ -87,9 +87,13 @@ struct DevScalars {
   unsigned long long phase_ns[4];
   // in-region device timing of the two CG SpMV kernels (bench marks): [0] z = R_y^-1 A p,
   // [1] Gp = A'z + P p + R_x p.  Start = first CTA's first instruction, end = last CTA done.
-  int kt_on, kt_pad;
+  int kt_on;
+  // row-partitioned mode: 1 => grid reductions park their raw sums / maxes in part[] and the
+  // consuming formula runs in k_apply_fin after the NCCL all-reduce (see dist_finish)
+  int dist;
   unsigned int kt_ticket[2], kt_cnt[2];
   unsigned long long kt_start[2], kt_ns[2];
+  double part[kMaxRedVals];
 };
 
 // indices into DevScalars::res
@@ -106,6 +110,7 @@ enum ResIdx {
 struct Ctx {
   int device = 0;
   int sms = 148;
+  bool dist = false;  // workspace of a row-partitioned solve (dist.cuh)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   RedWs red{nullptr, nullptr, 0};
@@ -114,6 +119,7 @@ struct Ctx {
   cudaEvent_t ev = nullptr;
   // counters
   long long launches = 0, spmv_calls = 0, h2d = 0, d2h = 0;
+  long long collectives = 0, collective_bytes = 0;  // NCCL all-reduces issued / bytes reduced (dist mode)
   int grid_ew() const { return sms * kCtasPerSm; }
 
   int init(int dev) {
@@ -298,6 +304,24 @@ __device__ __forceinline__ void grid_reduce(double *vals, const RedWs &ws, Fin f
     *ws.ticket = 0u;
     __threadfence();
   }
+}
+// grid_reduce whose finalising formula `fin` (a functor, constructible on the host as well)
+// either runs in place (single GPU) or is deferred until the raw values have been all-reduced
+// across the ranks of a row-partitioned solve.
+template <int NS, int NM, class Fin>
+__device__ __forceinline__ void grid_reduce_fin(double *vals, const RedWs &ws, DevScalars *S, Fin fin) {
+  grid_reduce<NS, NM>(vals, ws, [S, fin](double *o) {
+    if (S->dist) {
+#pragma unroll
+      for (int k = 0; k < NS + NM; ++k) S->part[k] = o[k];
+    } else {
+      fin(o, S);
+    }
+  });
+}
+template <class Fin>
+__global__ void k_apply_fin(Fin fin, DevScalars *S) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) fin(S->part, S);
 }
 #endif  // __CUDACC__
 

@@ -1,4 +1,5 @@
 // linsys.cu -- PCG kernels, the LinSys driver and the ScsLinSysWork plugin ABI.
+#include "dist.cuh"
 #include "linsys.cuh"
 
 namespace b200 {
@@ -35,9 +36,11 @@ struct EpiG {
   double *Gp;
   const double *p, *rx;
   DevScalars *S_;
+  const double *extra;  // row-partitioned mode: all-reduced A'z (acc then only holds P p), else null
   __device__ __forceinline__ void init(State &s) const { s.pgp = 0.0; kt_begin(S_, 1); }
   __device__ __forceinline__ void row(State &s, int j, double acc) const {
     const double pj = p[j];
+    if (extra) acc += extra[j];
     const double g = acc + rx[j] * pj;
     Gp[j] = g;
     s.pgp = fma(pj, g, s.pgp);
@@ -61,9 +64,11 @@ struct EpiG0 {
   const double *s, *rx, *M;
   double *r, *z, *p;
   CgCtl ctl;
+  const double *extra;  // row-partitioned mode: all-reduced A' R_y^-1 A s (may alias r), else null
   __device__ __forceinline__ void init(State &st) const { st.ztr = 0.0; st.nr = 0.0; }
   __device__ __forceinline__ void row(State &st, int j, double acc) const {
     const double sj = s[j];
+    if (extra) acc += extra[j];
     const double rj = b[j] - (acc + rx[j] * sj);
     const double zj = rj * M[j];
     b[j] = sj;
@@ -179,17 +184,33 @@ __global__ void __launch_bounds__(kThreads) k_zero_if(double *__restrict__ b, in
 }
 
 // S->cg_tol = tol ; zero_rhs = (||b||_inf <= 1e-12) ; cg_done = zero_rhs ; cg_its = 0
+struct FinPrepareFlags {
+  double tol;
+  __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    S->cg_tol = tol;
+    S->zero_rhs = (o[0] <= 1e-12) ? 1 : 0;
+    S->cg_done = S->zero_rhs;
+    S->cg_its = 0;
+  }
+};
 __global__ void __launch_bounds__(kThreads)
 k_prepare_flags(const double *__restrict__ b, int len, double tol, RedWs ws, DevScalars *S) {
   double v[1] = {0.0};
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x)
     v[0] = fmax(v[0], fabs(b[j]));
-  grid_reduce<0, 1>(v, ws, [S, tol](double *o) {
-    S->cg_tol = tol;
-    S->zero_rhs = (o[0] <= 1e-12) ? 1 : 0;
-    S->cg_done = S->zero_rhs;
-    S->cg_its = 0;
-  });
+  grid_reduce_fin<0, 1>(v, ws, S, FinPrepareFlags{tol});
+}
+
+// row-partitioned mode helpers: b[j] += a[j] ; M = 1 / ((rx + colsum) + Pdiag)
+__global__ void __launch_bounds__(kThreads)
+k_add_if(double *__restrict__ b, const double *__restrict__ a, int n, const int *skip) {
+  if (*skip) return;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) b[j] += a[j];
+}
+__global__ void __launch_bounds__(kThreads)
+k_precond_fin(double *__restrict__ M, const double *__restrict__ rx, const double *__restrict__ Pdiag, int n) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    M[j] = 1.0 / ((rx[j] + M[j]) + Pdiag[j]);
 }
 
 // ---------------------------------------------------------------------------- driver ---
@@ -223,6 +244,7 @@ int LinSys::init(Ctx *ctx, const ScsMatrix *Ah, const ScsMatrix *Ph) {
   if (c->sync()) return -1;
   if (chunks_build(*c, chA, A, nullptr)) return -1;
   if (chunks_build(*c, chAt, At, hasP ? &P : nullptr)) return -1;
+  if (c->dist && chunks_build(*c, chP, P, nullptr)) return -1;
   {
     const long long mi = 10ll * n;  // private.c:299
     const int mi32 = mi > 0x7fffffffLL ? 0x7fffffff : (int)mi;
@@ -246,6 +268,7 @@ void LinSys::destroy() {
   csr_free(P);
   chunks_free(chA);
   chunks_free(chAt);
+  chunks_free(chP);
   if (own_diag_r) dev_free(diag_r);
   diag_r = nullptr;
   dev_free(Pdiag);
@@ -267,9 +290,19 @@ int LinSys::update_precond() {
     k_extract_diag<<<ew_grid(*c, n), kThreads, 0, c->stream>>>(P, Pdiag);
     c->launches++;
   }
+  ElemSqDiv e{diag_r + n};
+  if (c->dist) {  // column sums of the local rows, summed over the ranks, then the same formula
+    EpiStore es; es.y = M;
+    row_kernel<ElemSqDiv, ElemSqDiv, EpiStore, false>
+        <<<chAt.grid, kThreads, 0, c->stream>>>(At, e, At, e, chAt.d, chAt.n, es, c->red, c->S, nullptr);
+    if (dist_allreduce(*c, M, (size_t)n, 0)) return -1;
+    k_precond_fin<<<ew_grid(*c, n), kThreads, 0, c->stream>>>(M, diag_r, Pdiag, n);
+    c->launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   EpiPrecond epi;
   epi.M = M; epi.rx = diag_r; epi.Pdiag = Pdiag;
-  ElemSqDiv e{diag_r + n};
   row_kernel<ElemSqDiv, ElemSqDiv, EpiPrecond, false>
       <<<chAt.grid, kThreads, 0, c->stream>>>(At, e, At, e, chAt.d, chAt.n, epi, c->red, c->S, nullptr);
   c->launches++;
@@ -290,9 +323,21 @@ int LinSys::launch_A_scaled(const double *x, double *out, const int *skip, int t
 
 int LinSys::launch_G(const double *zin, const double *pin, double *out, const int *skip, int tag, bool counted) {
   EpiG epi;
-  epi.Gp = out; epi.p = pin; epi.rx = diag_r; epi.S_ = c->S;
+  epi.Gp = out; epi.p = pin; epi.rx = diag_r; epi.S_ = c->S; epi.extra = nullptr;
   ElemMul ea{zin}, eb{pin};
   (void)tag;
+  if (c->dist) {
+    // out = A_g' z_g (local rows), summed over the ranks; then P p + R_x p and p'Gp on every rank
+    EpiStore es; es.y = out;
+    row_kernel<ElemMul, ElemMul, EpiStore, false>
+        <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, At, ea, chAt.d, chAt.n, es, c->red, c->S, skip);
+    if (dist_allreduce(*c, out, (size_t)n, 0)) return -1;
+    epi.extra = out;
+    row_kernel<ElemMul, ElemMul, EpiG, false>
+        <<<chP.grid, kThreads, 0, c->stream>>>(P, eb, P, eb, chP.d, chP.n, epi, c->red, c->S, skip);
+    if (counted) { c->launches += 2; c->spmv_calls += 2; }
+    return 0;
+  }
   if (hasP)
     row_kernel<ElemMul, ElemMul, EpiG, true>
         <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, P, eb, chAt.d, chAt.n, epi, c->red, c->S, skip);
@@ -306,7 +351,7 @@ int LinSys::launch_G(const double *zin, const double *pin, double *out, const in
 int LinSys::prepare_flags(const double *b, double tol) {
   k_prepare_flags<<<ew_grid(*c, n + m), kThreads, 0, c->stream>>>(b, n + m, tol, c->red, c->S);
   c->launches++;
-  return 0;
+  return dist_finish(*c, 0, 1, FinPrepareFlags{tol});
 }
 
 int LinSys::enqueue_head(double *b, const double *ws, CgCtl ctl) {
@@ -317,7 +362,15 @@ int LinSys::enqueue_head(double *b, const double *ws, CgCtl ctl) {
   cudaStream_t st = cx.stream;
   // tmp = R_y^-1 ry ; b[:n] += A' tmp
   k_scale_ry<<<gm, kThreads, 0, st>>>(b + n, diag_r + n, tmp, m, done);
-  {
+  if (cx.dist) {
+    EpiStore es; es.y = z;  // z is free until CG starts
+    ElemMul e{tmp};
+    row_kernel<ElemMul, ElemMul, EpiStore, false>
+        <<<chAt.grid, kThreads, 0, st>>>(At, e, At, e, chAt.d, chAt.n, es, cx.red, S, done);
+    if (dist_allreduce(cx, z, (size_t)n, 0)) return -1;
+    k_add_if<<<gn, kThreads, 0, st>>>(b, z, n, done);
+    cx.launches++;
+  } else {
     EpiRhs epi; epi.b = b;
     ElemMul e{tmp};
     row_kernel<ElemMul, ElemMul, EpiRhs, false>
@@ -328,8 +381,18 @@ int LinSys::enqueue_head(double *b, const double *ws, CgCtl ctl) {
     launch_A_scaled(ws, tmp, done);
     EpiG0 epi;
     epi.b = b; epi.s = ws; epi.rx = diag_r; epi.M = M; epi.r = r; epi.z = z; epi.p = p; epi.ctl = ctl;
+    epi.extra = nullptr;
     ElemMul ea{tmp}, eb{ws};
-    if (hasP)
+    if (cx.dist) {
+      EpiStore es; es.y = r;
+      row_kernel<ElemMul, ElemMul, EpiStore, false>
+          <<<chAt.grid, kThreads, 0, st>>>(At, ea, At, ea, chAt.d, chAt.n, es, cx.red, S, done);
+      if (dist_allreduce(cx, r, (size_t)n, 0)) return -1;
+      epi.extra = r;
+      row_kernel<ElemMul, ElemMul, EpiG0, false>
+          <<<chP.grid, kThreads, 0, st>>>(P, eb, P, eb, chP.d, chP.n, epi, cx.red, S, done);
+      cx.launches++;
+    } else if (hasP)
       row_kernel<ElemMul, ElemMul, EpiG0, true>
           <<<chAt.grid, kThreads, 0, st>>>(At, ea, P, eb, chAt.d, chAt.n, epi, cx.red, S, done);
     else

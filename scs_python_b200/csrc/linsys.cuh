@@ -26,6 +26,11 @@ struct LinSys {
   CsrDev A, At, P;  // CSR(A): m rows; CSR(A'): n rows; full symmetric CSR(P): n rows
   bool hasP = false;
   ChunkList chA, chAt;   // chAt is built over the fused (A', P) rows
+  // row-partitioned mode: chunk list over the n rows of P alone.  P is replicated, so this
+  // list -- and with it the summation order of every reduction over replicated n-space data
+  // (p'Gp, z'r, x'Px ...) -- is identical on all ranks, which keeps the CG scalars and hence
+  // the ranks' control flow bit-identical.
+  ChunkList chP;
   double *diag_r = nullptr;  // n+m(+1) on device; owned iff own_diag_r
   bool own_diag_r = false;
   double *Pdiag = nullptr;  // n (zeros when !hasP)

@@ -17,12 +17,14 @@
 //   AaDev       Anderson acceleration (aa.cu)
 //
 // Only the residual scalar block and one CG stop flag per iteration cross to the host.
+#include <algorithm>
 #include <chrono>
 #include <csignal>
 #include <string>
 
 #include "aa.cuh"
 #include "cones.cuh"
+#include "dist.cuh"
 #include "linsys.cuh"
 
 namespace b200 {
@@ -129,6 +131,14 @@ struct EpiStoreComb : EpiNoState {
   __device__ __forceinline__ void row(State &, int r, double acc) const { y[r] = acc; }
 };
 
+struct FinSigma {  // normalize.c:46-52
+  __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    double sigma = fmax(o[0], o[1]);
+    sigma = sigma < kMinNormFactor ? 1.0 : sigma;
+    sigma = sigma > kMaxNormFactor ? kMaxNormFactor : sigma;
+    S->sigma = sigma < kDivEps ? 1.0 / kDivEps : 1.0 / sigma;
+  }
+};
 // b *= D ; c *= E ; sigma from the inf-norms (normalize.c:33-52)
 __global__ void __launch_bounds__(kThreads)
 k_scale_bc(double *__restrict__ b, const double *__restrict__ D, int m, double *__restrict__ c,
@@ -145,12 +155,7 @@ k_scale_bc(double *__restrict__ b, const double *__restrict__ D, int m, double *
       v[1] = fmax(v[1], fabs(t));
     }
   }
-  grid_reduce<0, 2>(v, ws, [S](double *o) {
-    double sigma = fmax(o[0], o[1]);
-    sigma = sigma < kMinNormFactor ? 1.0 : sigma;
-    sigma = sigma > kMaxNormFactor ? kMaxNormFactor : sigma;
-    S->sigma = sigma < kDivEps ? 1.0 / kDivEps : 1.0 / sigma;
-  });
+  grid_reduce_fin<0, 2>(v, ws, S, FinSigma{});
 }
 __global__ void __launch_bounds__(kThreads)
 k_scale_sigma(double *__restrict__ b, int m, double *__restrict__ c, int n, const DevScalars *S) {
@@ -193,19 +198,31 @@ k_warm_start(double *__restrict__ v, const double *__restrict__ x, const double 
   }
 }
 
+struct FinPrep {  // CG tolerance rule, scs.c:706-719 ; zero right-hand side, private.c:288-291
+  __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    double tol = fmin(S->nm_ax_s_btau, S->nm_px_aty_ctau);
+    const double nm_ws = o[0] / pow((double)S->iter + 1.0, kCgRate);
+    tol = kCgTolFactor * fmin(tol, nm_ws);
+    S->cg_tol = fmax(kCgBestTol, tol);
+    S->zero_rhs = (o[1] <= 1e-12) ? 1 : 0;
+    S->cg_done = S->zero_rhs;
+    S->cg_its = 0;
+  }
+};
 // normalize_v, v_prev copy, RHS, warm start, CG tolerance and flags
 template <bool ACCEL>
 __global__ void __launch_bounds__(kThreads)
 k_prep(double *__restrict__ v, double *__restrict__ v_prev, double *__restrict__ u_t, const double *__restrict__ u,
        const double *__restrict__ g, const double *__restrict__ R, double *__restrict__ ws, int n, int m,
-       RedWs red, DevScalars *S) {
+       int l_total, RedWs red, DevScalars *S) {
   const int l = n + m + 1;
   const int it = S->iter;
   if (blockIdx.x == 0 && threadIdx.x == 0) phase_lap(S, -1);  // lin-sys interval starts
   double sc = 1.0;
   if (it >= kFeasibleIters) {
     const double vn = sqrt(S->vnorm2);
-    if (vn != 0.0) sc = sqrt((double)l) / vn;  // ITERATE_NORM == 1
+    // ITERATE_NORM == 1; l_total = length of the whole iterate (== l unless row-partitioned)
+    if (vn != 0.0) sc = sqrt((double)l_total) / vn;
   }
   const double tau_u = u[l - 1];
   double mx[2] = {0.0, 0.0};  // ||ws||_inf, ||rhs||_inf
@@ -228,34 +245,14 @@ k_prep(double *__restrict__ v, double *__restrict__ v_prev, double *__restrict__
       u_t[j] = vj;
     }
   }
-  grid_reduce<0, 2>(mx, red, [S, it](double *o) {
-    double tol = fmin(S->nm_ax_s_btau, S->nm_px_aty_ctau);
-    const double nm_ws = o[0] / pow((double)it + 1.0, kCgRate);
-    tol = kCgTolFactor * fmin(tol, nm_ws);
-    S->cg_tol = fmax(kCgBestTol, tol);
-    S->zero_rhs = (o[1] <= 1e-12) ? 1 : 0;
-    S->cg_done = S->zero_rhs;
-    S->cg_its = 0;
-  });
+  grid_reduce_fin<0, 2>(mx, red, S, FinPrep{});
 }
 
-// root_plus (scs.c:667-688): p = u_t (after the solve), mu = v, eta = v[l-1]
-__global__ void __launch_bounds__(kThreads)
-k_rootplus(const double *__restrict__ u_t, const double *__restrict__ v, const double *__restrict__ g,
-           const double *__restrict__ R, int nm, RedWs red, DevScalars *S) {
-  const int it = S->iter;
-  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nm; j += gridDim.x * blockDim.x) {
-    const double ri = R[j], gi = g[j], pi = u_t[j], mui = v[j];
-    s[0] = fma(gi * gi, ri, s[0]);
-    s[1] = fma(mui * gi, ri, s[1]);
-    s[2] = fma(pi * gi, ri, s[2]);
-    s[3] = fma(pi * pi, ri, s[3]);
-    s[4] = fma(pi * mui, ri, s[4]);
-  }
-  const double eta = v[nm], tau_scale = R[nm];
-  grid_reduce<5, 0>(s, red, [S, it, eta, tau_scale](double *o) {
-    if (it < kFeasibleIters) {
+struct FinRootPlus {  // the quadratic of scs.c:676-687
+  const double *eta_ptr, *tau_scale_ptr;  // v[l-1], diag_r[l-1]
+  __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    const double eta = *eta_ptr, tau_scale = *tau_scale_ptr;
+    if (S->iter < kFeasibleIters) {
       S->tau = 1.0;
     } else {
       const double a = tau_scale + o[0];
@@ -265,7 +262,23 @@ k_rootplus(const double *__restrict__ u_t, const double *__restrict__ v, const d
       S->tau = (-b + sqrt(fmax(rad, 0.0))) / (2 * a);
     }
     phase_lap(S, 0);  // lin-sys interval ends, cone interval starts
-  });
+  }
+};
+// root_plus (scs.c:667-688): p = u_t (after the solve), mu = v, eta = v[l-1]
+__global__ void __launch_bounds__(kThreads)
+k_rootplus(const double *__restrict__ u_t, const double *__restrict__ v, const double *__restrict__ g,
+           const double *__restrict__ R, int n, int nm, int own_x, RedWs red, DevScalars *S) {
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  // own_x == 0: rank > 0 of a row-partitioned solve, the replicated x block is summed by rank 0
+  for (int j = (own_x ? 0 : n) + blockIdx.x * blockDim.x + threadIdx.x; j < nm; j += gridDim.x * blockDim.x) {
+    const double ri = R[j], gi = g[j], pi = u_t[j], mui = v[j];
+    s[0] = fma(gi * gi, ri, s[0]);
+    s[1] = fma(mui * gi, ri, s[1]);
+    s[2] = fma(pi * gi, ri, s[2]);
+    s[3] = fma(pi * pi, ri, s[3]);
+    s[4] = fma(pi * mui, ri, s[4]);
+  }
+  grid_reduce_fin<5, 0>(s, red, S, FinRootPlus{v + nm, R + nm});
 }
 
 // u_t -= tau g ; u = 2 u_t - v ; zero / nonneg rows done, other rows pre-scaled by -R with
@@ -299,11 +312,17 @@ k_pre(double *__restrict__ u_t, double *__restrict__ u, double *__restrict__ rsk
   }
 }
 
+struct FinPost {
+  __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    S->vnorm2 = o[0];
+    S->iter += 1;  // the iteration index lives on the device: the graph re-launches unchanged
+  }
+};
 // MODE 0: rsk and dual step ; 1: rsk only ; 2: dual step only   (scs.c:739-751)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_post(double *__restrict__ v, double *__restrict__ rsk, const double *__restrict__ u, const double *__restrict__ u_t,
-       const double *__restrict__ R, int l, double alpha, RedWs red, DevScalars *S) {
+       const double *__restrict__ R, int n, int l, int own_x, double alpha, RedWs red, DevScalars *S) {
   if (MODE != 2 && blockIdx.x == 0 && threadIdx.x == 0) phase_lap(S, 1);  // cone interval ends
   double s[1] = {0.0};
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x) {
@@ -312,14 +331,11 @@ k_post(double *__restrict__ v, double *__restrict__ rsk, const double *__restric
     if (MODE != 1) {
       const double vn = fma(alpha, uj - utj, vj);
       v[j] = vn;
-      s[0] = fma(vn, vn, s[0]);
+      // own_x == 0: the replicated x block and tau are summed by rank 0 only
+      if (own_x || (j >= n && j < l - 1)) s[0] = fma(vn, vn, s[0]);
     }
   }
-  if (MODE != 1)
-    grid_reduce<1, 0>(s, red, [S](double *o) {
-      S->vnorm2 = o[0];
-      S->iter += 1;  // the iteration index lives on the device: the graph re-launches unchanged
-    });
+  if (MODE != 1) grid_reduce_fin<1, 0>(s, red, S, FinPost{});
 }
 
 // phase clock boundary around the acceleration kernels: slot < 0 opens, slot >= 0 closes
@@ -334,6 +350,22 @@ k_remap_v(double *__restrict__ v, const double *__restrict__ rsk, const double *
 }
 
 // ---- residual epilogues (scs.c:513-585 and 465-509) ----
+struct FinResA {
+  const double *tau_ptr, *kap_ptr;
+  __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    S->res[R_TAU] = fabs(*tau_ptr);
+    S->res[R_KAP] = fabs(*kap_ptr);
+    S->res[R_BTY_TAU] = o[0];
+    S->res[R_NM_AX_S_BTAU] = o[1];
+    S->res[R_NM_AX_S] = o[2];
+    S->res[R_NM_AX] = o[3];
+    S->res[R_ONM_AX_S_BTAU] = o[4];
+    S->res[R_ONM_AX_S] = o[5];
+    S->res[R_ONM_AX] = o[6];
+    S->res[R_ONM_S] = o[7];
+    S->nm_ax_s_btau = o[1];
+  }
+};
 // primal pass over CSR(A), gather x = u[0:n]
 struct EpiResA {
   static constexpr bool kSeparate = false;
@@ -364,21 +396,7 @@ struct EpiResA {
   }
   __device__ __forceinline__ void finish(State &st, const RedWs &ws, DevScalars *S) const {
     double v[8] = {st.bty, st.m[0], st.m[1], st.m[2], st.m[3], st.m[4], st.m[5], st.m[6]};
-    const double *uu = u, *rr = rsk;
-    const int l1 = n + m_;
-    grid_reduce<1, 7>(v, ws, [S, uu, rr, l1](double *o) {
-      S->res[R_TAU] = fabs(uu[l1]);
-      S->res[R_KAP] = fabs(rr[l1]);
-      S->res[R_BTY_TAU] = o[0];
-      S->res[R_NM_AX_S_BTAU] = o[1];
-      S->res[R_NM_AX_S] = o[2];
-      S->res[R_NM_AX] = o[3];
-      S->res[R_ONM_AX_S_BTAU] = o[4];
-      S->res[R_ONM_AX_S] = o[5];
-      S->res[R_ONM_AX] = o[6];
-      S->res[R_ONM_S] = o[7];
-      S->nm_ax_s_btau = o[1];
-    });
+    grid_reduce_fin<1, 7>(v, ws, S, FinResA{u + n + m_, rsk + n + m_});
   }
 };
 // dual pass over (CSR(A'), CSR(P)), gathers y = u[n:] and x = u[0:n]
@@ -388,12 +406,16 @@ struct EpiResAt {
   const double *u, *c, *E;
   int n, m_;
   double inv_ps;
+  const double *extra;  // row-partitioned mode: all-reduced A'y (the kernel then runs over P only), else null
   __device__ __forceinline__ void init(State &s) const {
     s.xpx = 0.0; s.ctx = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) s.m[k] = 0.0;
   }
-  __device__ __forceinline__ void row(State &st, int j, double aty) const { row2(st, j, aty, 0.0); }
+  __device__ __forceinline__ void row(State &st, int j, double acc) const {
+    if (extra) row2(st, j, extra[j], acc);  // acc = (P x)_j
+    else row2(st, j, acc, 0.0);             // acc = (A'y)_j, no P
+  }
   __device__ __forceinline__ void row2(State &st, int j, double aty, double px) const {
     const double tau = fabs(u[n + m_]);
     const double xj = u[j], cj = c[j];
@@ -424,6 +446,13 @@ struct EpiResAt {
   }
 };
 
+struct FinSol {
+  __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    S->fin[2] = o[0];
+    S->fin[0] = o[1];
+    S->fin[1] = o[2];
+  }
+};
 // un-normalised solution (normalize.c:78-90) + ||s||_inf, ||y||_inf, s'y (scs.c:885-887)
 __global__ void __launch_bounds__(kThreads)
 k_finalize_sol(double *__restrict__ xo, double *__restrict__ yo, double *__restrict__ so, const double *__restrict__ u,
@@ -444,11 +473,7 @@ k_finalize_sol(double *__restrict__ xo, double *__restrict__ yo, double *__restr
       v[2] = fmax(v[2], fabs(y));
     }
   }
-  grid_reduce<1, 2>(v, red, [S](double *o) {
-    S->fin[2] = o[0];
-    S->fin[0] = o[1];
-    S->fin[1] = o[2];
-  });
+  grid_reduce_fin<1, 2>(v, red, S, FinSol{});
 }
 __global__ void __launch_bounds__(kThreads)
 k_scale3(double *__restrict__ x, int n, double fx, double *__restrict__ y, double *__restrict__ s, int m, double fy,
@@ -498,6 +523,10 @@ struct SCS_WORK {
   cudaStream_t st_body = nullptr;
   long long graph_launches = 0, graph_spmv = 0;  // fixed (non-CG-loop) kernels per graph launch
   long long n_checks = 0, n_aa = 0;               // residual checks / AA applications so far
+  // row-partitioned mode (dist.cuh): this rank owns rows [row0, row0 + m) of the m_total rows
+  bool dist = false;
+  int rank = 0, world = 1, m_total = 0, row0 = 0, own_x = 1;
+  double *gather = nullptr;  // m_total doubles: assembling the full y / s on every rank
   ScsSettings stgs;
   std::string write_fn, csv_fn;
   // device state
@@ -730,6 +759,7 @@ static int normalize_a_p_dev(SCS_WORK *w) {
       else
         row_kernel<ElemAbsMax, ElemAbsMax, EpiStoreComb, false>
             <<<ls.chAt.grid, kThreads, 0, st>>>(ls.At, e, ls.P, e, ls.chAt.d, ls.chAt.n, eE, c.red, c.S, nullptr);
+      if (dist_allreduce(c, Et, (size_t)n, 1)) return -1;  // column inf-norms over all ranks' rows
       k_inv_sqrt_limit<<<ew_grid(c, n), kThreads, 0, st>>>(Et, n, 0);
       c.launches += 4;
     } else {
@@ -739,12 +769,13 @@ static int normalize_a_p_dev(SCS_WORK *w) {
       k_sqrt<<<ew_grid(c, m), kThreads, 0, st>>>(Dt, m);
       if (w->cone.enforce_boundaries(Dt, 1)) return -1;
       k_inv_sqrt_limit<<<ew_grid(c, m), kThreads, 0, st>>>(Dt, m, 0);
-      if (ls.hasP)
+      if (ls.hasP && w->own_x)  // P is replicated: its squares are summed by rank 0 only
         row_kernel<ElemSumSq, ElemSumSq, EpiStoreComb, true>
             <<<ls.chAt.grid, kThreads, 0, st>>>(ls.At, e, ls.P, e, ls.chAt.d, ls.chAt.n, eE, c.red, c.S, nullptr);
       else
         row_kernel<ElemSumSq, ElemSumSq, EpiStoreComb, false>
             <<<ls.chAt.grid, kThreads, 0, st>>>(ls.At, e, ls.P, e, ls.chAt.d, ls.chAt.n, eE, c.red, c.S, nullptr);
+      if (dist_allreduce(c, Et, (size_t)n, 0)) return -1;  // column sums of squares over all ranks' rows
       k_inv_sqrt_limit<<<ew_grid(c, n), kThreads, 0, st>>>(Et, n, 1);
       c.launches += 5;
     }
@@ -790,12 +821,23 @@ static int populate_residuals(SCS_WORK *w, int iter) {
     ElemMul e{w->u};
     row_kernel<ElemMul, ElemMul, EpiResA, false>
         <<<ls.chA.grid, kThreads, 0, c.stream>>>(ls.A, e, ls.A, e, ls.chA.d, ls.chA.n, epi, c.red, c.S, nullptr);
+    if (dist_finish(c, 1, 7, FinResA{w->u + n + m, w->rsk + n + m})) return -1;
   }
   {
     EpiResAt epi;
     epi.u = w->u; epi.c = w->cvec; epi.E = w->E; epi.n = n; epi.m_ = m; epi.inv_ps = 1.0 / w->primal_scale;
+    epi.extra = nullptr;
     ElemMul ea{w->u + n}, eb{w->u};
-    if (ls.hasP)
+    if (c.dist) {  // A_g' y_g summed over the ranks, then the P pass with the same epilogue
+      EpiStore es; es.y = ls.Gp;
+      row_kernel<ElemMul, ElemMul, EpiStore, false>
+          <<<ls.chAt.grid, kThreads, 0, c.stream>>>(ls.At, ea, ls.At, ea, ls.chAt.d, ls.chAt.n, es, c.red, c.S, nullptr);
+      if (dist_allreduce(c, ls.Gp, (size_t)n, 0)) return -1;
+      epi.extra = ls.Gp;
+      row_kernel<ElemMul, ElemMul, EpiResAt, false>
+          <<<ls.chP.grid, kThreads, 0, c.stream>>>(ls.P, eb, ls.P, eb, ls.chP.d, ls.chP.n, epi, c.red, c.S, nullptr);
+      c.launches++; c.spmv_calls++;
+    } else if (ls.hasP)
       row_kernel<ElemMul, ElemMul, EpiResAt, true>
           <<<ls.chAt.grid, kThreads, 0, c.stream>>>(ls.At, ea, ls.P, eb, ls.chAt.d, ls.chAt.n, epi, c.red, c.S, nullptr);
     else
@@ -951,12 +993,14 @@ static void mark_close(SCS_WORK *w, int iter) {
 static int enqueue_front_head(SCS_WORK *w, CgCtl loop) {
   Ctx &c = w->c;
   const int n = w->n, m = w->m, gl = ew_grid(c, w->l);
+  const int l_total = w->dist ? n + w->m_total + 1 : w->l;
   cudaStream_t st = c.stream;
   if (w->has_aa)
-    k_prep<true><<<gl, kThreads, 0, st>>>(w->v, w->v_prev, w->u_t, w->u, w->g, w->diag_r, w->ws, n, m, c.red, c.S);
+    k_prep<true><<<gl, kThreads, 0, st>>>(w->v, w->v_prev, w->u_t, w->u, w->g, w->diag_r, w->ws, n, m, l_total, c.red, c.S);
   else
-    k_prep<false><<<gl, kThreads, 0, st>>>(w->v, w->v_prev, w->u_t, w->u, w->g, w->diag_r, w->ws, n, m, c.red, c.S);
+    k_prep<false><<<gl, kThreads, 0, st>>>(w->v, w->v_prev, w->u_t, w->u, w->g, w->diag_r, w->ws, n, m, l_total, c.red, c.S);
   c.launches++;
+  if (dist_finish(c, 0, 2, FinPrep{})) return -1;
   return w->ls.enqueue_head(w->u_t, w->ws, loop);
 }
 static int enqueue_front_tail(SCS_WORK *w) {
@@ -964,7 +1008,8 @@ static int enqueue_front_tail(SCS_WORK *w) {
   const int n = w->n, m = w->m, gl = ew_grid(c, w->l);
   cudaStream_t st = c.stream;
   if (w->ls.enqueue_tail(w->u_t)) return -1;
-  k_rootplus<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->u_t, w->v, w->g, w->diag_r, n + m, c.red, c.S);
+  k_rootplus<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->u_t, w->v, w->g, w->diag_r, n, n + m, w->own_x, c.red, c.S);
+  if (dist_finish(c, 5, 0, FinRootPlus{w->v + n + m, w->diag_r + n + m})) return -1;
   k_pre<<<gl, kThreads, 0, st>>>(w->u_t, w->u, w->rsk, w->v, w->g, w->diag_r, n, m, w->cone.z, w->cone.z + w->cone.l, c.S);
   c.launches += 2;
   if (w->cone.has_nonlinear()) {
@@ -979,6 +1024,7 @@ static int build_iter_graph(SCS_WORK *w) {
   Ctx &c = w->c;
   const char *env = getenv("SCS_B200_NO_GRAPH");
   if (env && env[0] == '1') return 0;
+  if (w->dist) return 0;  // NCCL all-reduces sit inside the CG loop: stream launches, host-read stop flag
   cudaStream_t st = c.stream;
   const long long l0 = c.launches, s0 = c.spmv_calls;
   bool capturing = false, ok = false;
@@ -1053,7 +1099,7 @@ static void free_work(SCS_WORK *w) {
   if (w->st_body) cudaStreamDestroy(w->st_body);
   dev_free(w->u); dev_free(w->u_t); dev_free(w->v); dev_free(w->v_prev); dev_free(w->rsk); dev_free(w->g);
   dev_free(w->diag_r); dev_free(w->b); dev_free(w->cvec); dev_free(w->D); dev_free(w->E); dev_free(w->ws);
-  dev_free(w->sol_x); dev_free(w->sol_y); dev_free(w->sol_s);
+  dev_free(w->sol_x); dev_free(w->sol_y); dev_free(w->sol_s); dev_free(w->gather);
   w->c.destroy();
   delete w;
 }
@@ -1101,6 +1147,117 @@ static void fill_aa_stats(SCS_WORK *w, ScsInfo *info) {
   }
 }
 
+
+// ------------------------------------------------------------- row partition (dist) ---
+// Rank g of a row-partitioned solve owns a contiguous block of rows of A.  Cuts may fall on
+// any row of the zero / nonneg cones and otherwise only between cones, and are
+// placed so that every rank holds about the same number of non-zeros.
+struct LocalProblem {
+  std::vector<double> Ax, b;
+  std::vector<int> Ai, Ap;
+  ScsMatrix A;
+  ScsData d;
+  ScsCone k;
+  int row0 = 0, m = 0;
+};
+
+static int partition_rows(const ScsData *d, const ScsCone *k, int rank, int world, LocalProblem &out) {
+  const int m = d->m, n = d->n;
+  const ScsMatrix *A = d->A;
+  std::vector<long long> pref((size_t)m + 1, 0);  // non-zeros in rows [0, i)
+  for (int t = 0; t < A->p[n]; ++t) pref[(size_t)A->i[t] + 1]++;
+  for (int i = 0; i < m; ++i) pref[(size_t)i + 1] += pref[(size_t)i];
+  // allowed cut positions beyond the z / l rows: cone boundaries
+  std::vector<int> bnd;
+  int off = k->z + k->l;
+  auto push = [&](int sz) { off += sz; bnd.push_back(off); };
+  if (k->bsize > 0) push(k->bsize);
+  for (int i = 0; i < k->qsize; ++i) push(k->q[i]);
+  for (int i = 0; i < k->ssize; ++i) push(k->s[i] * (k->s[i] + 1) / 2);
+  for (int i = 0; i < k->cssize; ++i) push(k->cs[i] * k->cs[i]);
+  for (int i = 0; i < k->ep + k->ed + k->psize; ++i) push(3);
+  const int zl = k->z + k->l;
+  auto next_allowed = [&](int pos) {  // smallest allowed cut >= pos
+    if (pos <= zl) return pos;
+    auto it = std::lower_bound(bnd.begin(), bnd.end(), pos);
+    return it == bnd.end() ? m : *it;
+  };
+  std::vector<int> cut((size_t)world + 1, 0);
+  cut[(size_t)world] = m;
+  const long long total = pref[(size_t)m];
+  for (int g = 1; g < world; ++g) {
+    const long long target = total * g / world;
+    int pos = (int)(std::lower_bound(pref.begin(), pref.end(), target) - pref.begin());
+    pos = next_allowed(pos);
+    if (pos <= cut[(size_t)g - 1]) pos = next_allowed(cut[(size_t)g - 1] + 1);
+    cut[(size_t)g] = pos > m ? m : pos;
+  }
+  for (int g = 0; g < world; ++g)
+    if (cut[(size_t)g + 1] <= cut[(size_t)g]) {
+      B200_PRINTF("ERROR: cannot cut %d rows into %d non-empty cone-aligned blocks\n", m, world);
+      return -1;
+    }
+  const int r0 = cut[(size_t)rank], r1 = cut[(size_t)rank + 1];
+  out.row0 = r0;
+  out.m = r1 - r0;
+  // local CSC: rows [r0, r1) of every column (row indices are sorted inside a column)
+  out.Ap.assign((size_t)n + 1, 0);
+  for (int j = 0; j < n; ++j) {
+    const int *b0 = A->i + A->p[j], *b1 = A->i + A->p[j + 1];
+    const int *lo = std::lower_bound(b0, b1, r0), *hi = std::lower_bound(b0, b1, r1);
+    out.Ap[(size_t)j + 1] = out.Ap[(size_t)j] + (int)(hi - lo);
+  }
+  out.Ai.resize((size_t)out.Ap[(size_t)n]);
+  out.Ax.resize((size_t)out.Ap[(size_t)n]);
+  for (int j = 0; j < n; ++j) {
+    const int *b0 = A->i + A->p[j], *b1 = A->i + A->p[j + 1];
+    const int lo = (int)(std::lower_bound(b0, b1, r0) - A->i), cnt = out.Ap[(size_t)j + 1] - out.Ap[(size_t)j];
+    for (int t = 0; t < cnt; ++t) {
+      out.Ai[(size_t)out.Ap[(size_t)j] + t] = A->i[lo + t] - r0;
+      out.Ax[(size_t)out.Ap[(size_t)j] + t] = A->x[lo + t];
+    }
+  }
+  out.b.assign(d->b + r0, d->b + r1);
+  out.A.x = out.Ax.data(); out.A.i = out.Ai.data(); out.A.p = out.Ap.data(); out.A.m = out.m; out.A.n = n;
+  out.d = *d;
+  out.d.m = out.m; out.d.A = &out.A; out.d.b = out.b.data();
+  // the cones inside [r0, r1)
+  ScsCone &lk = out.k;
+  lk = *k;
+  auto overlap = [&](int a0, int a1) { const int lo = a0 > r0 ? a0 : r0, hi = a1 < r1 ? a1 : r1; return hi > lo ? hi - lo : 0; };
+  lk.z = overlap(0, k->z);
+  lk.l = overlap(k->z, zl);
+  off = zl;
+  auto inside = [&](int start) { return start >= r0 && start < r1; };
+  if (k->bsize > 0) {
+    if (!inside(off)) { lk.bsize = 0; lk.bu = nullptr; lk.bl = nullptr; }
+    off += k->bsize;
+  }
+  auto take = [&](int count, auto size_of, int &first, int &num) {
+    first = -1; num = 0;
+    for (int i = 0; i < count; ++i) {
+      if (inside(off) && size_of(i) > 0) { if (first < 0) first = i; num++; }
+      else if (size_of(i) == 0 && first >= 0 && off < r1) num++;  // empty cones ride along
+      off += size_of(i);
+    }
+    if (first < 0) first = 0;
+  };
+  int f = 0, c = 0;
+  take(k->qsize, [&](int i) { return k->q[i]; }, f, c);
+  lk.q = k->q ? k->q + f : nullptr; lk.qsize = c;
+  take(k->ssize, [&](int i) { return k->s[i] * (k->s[i] + 1) / 2; }, f, c);
+  lk.s = k->s ? k->s + f : nullptr; lk.ssize = c;
+  take(k->cssize, [&](int i) { return k->cs[i] * k->cs[i]; }, f, c);
+  lk.cs = k->cs ? k->cs + f : nullptr; lk.cssize = c;
+  take(k->ep, [&](int) { return 3; }, f, c);
+  lk.ep = c;
+  take(k->ed, [&](int) { return 3; }, f, c);
+  lk.ed = c;
+  take(k->psize, [&](int) { return 3; }, f, c);
+  lk.p = k->p ? k->p + f : nullptr; lk.psize = c;
+  return 0;
+}
+
 }  // namespace b200
 
 // ==================================================================== public API ======
@@ -1135,10 +1292,11 @@ extern "C" scs_int scs_update(ScsWork *w, scs_float *b, scs_float *c) {  // scs.
   Ctx &cx = w->c;
   if (cudaSetDevice(cx.device) != cudaSuccess) return -1;
   const int n = w->n, m = w->m;
+  const int mt = w->dist ? w->m_total : m;  // b is always the caller's full-length vector
   if (b) {
-    if (w->b_orig.data() != b) memcpy(w->b_orig.data(), b, sizeof(double) * m);
+    if (w->b_orig.data() != b) memcpy(w->b_orig.data(), b, sizeof(double) * mt);
     double nm = 0.0;
-    for (int i = 0; i < m; ++i) nm = fmax(nm, fabs(b[i]));
+    for (int i = 0; i < mt; ++i) nm = fmax(nm, fabs(b[i]));
     w->nm_b_orig = nm;
   }
   if (c) {
@@ -1147,9 +1305,10 @@ extern "C" scs_int scs_update(ScsWork *w, scs_float *b, scs_float *c) {  // scs.
     for (int i = 0; i < n; ++i) nm = fmax(nm, fabs(c[i]));
     w->nm_c_orig = nm;
   }
-  if (h2d(cx, w->b, w->b_orig.data(), (size_t)m) || h2d(cx, w->cvec, w->c_orig.data(), (size_t)n)) return -1;
+  if (h2d(cx, w->b, w->b_orig.data() + w->row0, (size_t)m) || h2d(cx, w->cvec, w->c_orig.data(), (size_t)n)) return -1;
   if (w->stgs.normalize) {  // SCS(normalize_b_c), normalize.c:33-61
     k_scale_bc<<<ew_grid(cx, n + m), kThreads, 0, cx.stream>>>(w->b, w->D, m, w->cvec, w->E, n, cx.red, cx.S);
+    if (dist_finish(cx, 0, 2, FinSigma{})) return -1;
     k_scale_sigma<<<ew_grid(cx, n + m), kThreads, 0, cx.stream>>>(w->b, m, w->cvec, n, cx.S);
     cx.launches += 2;
     if (cx.fetch_scalars()) return -1;
@@ -1171,11 +1330,28 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
     return nullptr;
   }
   const Clock::time_point t0 = Clock::now();
-  if (stgs->verbose) print_init_header(d, k, stgs);
   SCS_WORK *w = new SCS_WORK();
+  w->stgs = *stgs;
+  const ScsData *d_full = d;
+  const ScsCone *k_full = k;
+  LocalProblem local;
+  Dist *dd = dist_current();
+  if (dd->on()) {  // keep rows [row0, row0 + m) of A, b and the cones inside them
+    if (partition_rows(d, k, dd->rank, dd->world, local)) { delete w; return nullptr; }
+    w->dist = true; w->rank = dd->rank; w->world = dd->world; w->own_x = dd->rank == 0;
+    w->m_total = d->m; w->row0 = local.row0;
+    d = &local.d;
+    k = &local.k;
+    if (dd->rank != 0) w->stgs.verbose = 0;
+    if (w->stgs.acceleration_lookback != 0) {
+      if (w->stgs.verbose) B200_PRINTF("NOTE: Anderson acceleration is switched off in the row-partitioned mode.\n");
+      w->stgs.acceleration_lookback = 0;
+    }
+    w->stgs.time_limit_secs = 0.;  // host clocks differ between ranks; the loop must stay collective
+  }
+  if (w->stgs.verbose) print_init_header(d_full, k_full, &w->stgs);
   w->n = d->n; w->m = d->m; w->l = d->n + d->m + 1;
   const int n = w->n, m = w->m, l = w->l;
-  w->stgs = *stgs;
   if (stgs->write_data_filename) w->write_fn = stgs->write_data_filename;
   if (stgs->log_csv_filename) w->csv_fn = stgs->log_csv_filename;
   w->stgs.write_data_filename = nullptr;  // rw.c is out of scope for this backend
@@ -1185,6 +1361,12 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
     if (w->c.init(current_device())) break;
     Ctx &c = w->c;
     cudaStream_t st = c.stream;
+    if (w->dist) {
+      c.dist = true;
+      const int one = 1;
+      if (cudaMemcpyAsync(&c.S->dist, &one, sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+      if (dev_alloc_zero(&w->gather, (size_t)w->m_total, st)) break;
+    }
     if (dev_alloc_zero(&w->u, (size_t)l, st) || dev_alloc_zero(&w->u_t, (size_t)l, st) ||
         dev_alloc_zero(&w->v, (size_t)l, st) || dev_alloc_zero(&w->v_prev, (size_t)l, st) ||
         dev_alloc_zero(&w->rsk, (size_t)l, st) || dev_alloc_zero(&w->g, (size_t)l, st) ||
@@ -1195,7 +1377,7 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
       B200_PRINTF("ERROR: work memory allocation failure\n");
       break;
     }
-    w->b_orig.assign((size_t)m, 0.0);
+    w->b_orig.assign((size_t)(w->dist ? w->m_total : m), 0.0);
     w->c_orig.assign((size_t)n, 0.0);
     if (w->cone.init(&w->c, k, m)) { B200_PRINTF("ERROR: init_cone failure\n"); break; }
     if (set_diag_r(w)) break;
@@ -1216,7 +1398,7 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
       }
       if (w->cone.normalize_box(Dh.empty() ? nullptr : Dh.data())) break;
     }
-    if (scs_update(w, d->b, d->c)) break;
+    if (scs_update(w, d_full->b, d->c)) break;
     if (w->ls.update_precond()) break;
     if (w->stgs.acceleration_lookback) {
       if (w->aa.init(&w->c, l, w->stgs.acceleration_lookback, w->stgs.acceleration_lookback,
@@ -1255,6 +1437,7 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   if (cudaSetDevice(c.device) != cudaSuccess) return SCS_FAILED;
   cudaStream_t st = c.stream;
   const int n = w->n, m = w->m, l = w->l;
+  const int m_out = w->dist ? w->m_total : m;  // length of the caller's y and s
   ScsSettings *stgs = &w->stgs;
   stgs->warm_start = warm_start;
   start_interrupt_listener();
@@ -1268,17 +1451,18 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   cudaMemsetAsync(&c.S->aa_rejected, 0, 2 * sizeof(int), st);  // safeguard counters of this solve
   if (warm_start) {
     if (!sol->x || !sol->y || !sol->s) {
-      return failure(w, m, n, sol, info, SCS_FAILED, "warm-start requested without x, y, s", "failure");
+      return failure(w, m_out, n, sol, info, SCS_FAILED, "warm-start requested without x, y, s", "failure");
     }
-    if (h2d(c, w->sol_x, sol->x, (size_t)n) || h2d(c, w->sol_y, sol->y, (size_t)m) || h2d(c, w->sol_s, sol->s, (size_t)m))
-      return failure(w, m, n, sol, info, SCS_FAILED, "warm-start upload", "failure");
+    if (h2d(c, w->sol_x, sol->x, (size_t)n) || h2d(c, w->sol_y, sol->y + w->row0, (size_t)m) ||
+        h2d(c, w->sol_s, sol->s + w->row0, (size_t)m))
+      return failure(w, m_out, n, sol, info, SCS_FAILED, "warm-start upload", "failure");
     k_warm_start<<<ew_grid(c, l), kThreads, 0, st>>>(w->v, w->sol_x, w->sol_y, w->sol_s, w->D, w->E, w->diag_r, n, m,
                                                      w->primal_scale, w->dual_scale);
   } else {
     k_cold_start<<<ew_grid(c, l), kThreads, 0, st>>>(w->v, l);
   }
   c.launches++;
-  if (update_work_cache(w)) return failure(w, m, n, sol, info, SCS_FAILED, "error in update_work_cache", "failure");
+  if (update_work_cache(w)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in update_work_cache", "failure");
   if (stgs->verbose) print_header();
 
   const int gl = ew_grid(c, l);
@@ -1299,7 +1483,7 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
     if (accel && i > 0 && i % interval == 0) {
       k_stamp<<<1, 1, 0, st>>>(c.S, -1);
       if (w->aa.apply(w->v, w->v_prev, &c.S->vnorm2))
-        return failure(w, m, n, sol, info, SCS_FAILED, "error in aa_apply", "failure");
+        return failure(w, m_out, n, sol, info, SCS_FAILED, "error in aa_apply", "failure");
       k_stamp<<<1, 1, 0, st>>>(c.S, 2);
       c.launches += 2;
       w->n_aa++;
@@ -1308,21 +1492,21 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
     //      enqueued on the stream with the CG loop driven from the host
     if (w->use_graph) {
       if (cudaGraphLaunch(w->gexec, st) != cudaSuccess)
-        return failure(w, m, n, sol, info, SCS_FAILED, "error launching the iteration graph", "failure");
+        return failure(w, m_out, n, sol, info, SCS_FAILED, "error launching the iteration graph", "failure");
       c.launches += w->graph_launches;
       c.spmv_calls += w->graph_spmv;
     } else {
       if (enqueue_front_head(w, CgCtl{}) || w->ls.solve_dev_loop(w->u_t, 0) || enqueue_front_tail(w))
-        return failure(w, m, n, sol, info, SCS_FAILED, "error in project_lin_sys / project_cones", "failure");
+        return failure(w, m_out, n, sol, info, SCS_FAILED, "error in project_lin_sys / project_cones", "failure");
     }
 
     const bool check = (i % kConvergedInterval == 0);
     const bool print = stgs->verbose && (i % kPrintInterval == 0);
     if (check || print) {
-      k_post<1><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, l, stgs->alpha, c.red, c.S);
+      k_post<1><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, n, l, w->own_x, stgs->alpha, c.red, c.S);
       c.launches++;
-      if (check && g_int_detected) return failure(w, m, n, sol, info, SCS_SIGINT, "interrupted", "interrupted");
-      if (populate_residuals(w, i)) return failure(w, m, n, sol, info, SCS_FAILED, "error in residuals", "failure");
+      if (check && g_int_detected && !w->dist) return failure(w, m_out, n, sol, info, SCS_SIGINT, "interrupted", "interrupted");
+      if (populate_residuals(w, i)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in residuals", "failure");
       w->n_checks++;
       if (check) {
         if ((info->status_val = has_converged(w)) != 0) break;
@@ -1333,19 +1517,21 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
       }
       if (print) print_summary(w, i, t0);
       if (stgs->adaptive_scale && i == w->r_o.last_iter) {
-        if (update_scale(w, i) < 0) return failure(w, m, n, sol, info, SCS_FAILED, "error in update_scale", "failure");
+        if (update_scale(w, i) < 0) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in update_scale", "failure");
       }
-      k_post<2><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, l, stgs->alpha, c.red, c.S);
+      k_post<2><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, n, l, w->own_x, stgs->alpha, c.red, c.S);
+      if (dist_finish(c, 1, 0, FinPost{})) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in the dual step", "failure");
       c.launches++;
     } else {
-      k_post<0><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, l, stgs->alpha, c.red, c.S);
+      k_post<0><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, n, l, w->own_x, stgs->alpha, c.red, c.S);
+      if (dist_finish(c, 1, 0, FinPost{})) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in the dual step", "failure");
       c.launches++;
     }
     // ---- AA safeguard (scs.c:1386-1394); the aa_norm > 0 gate is evaluated on the device
     if (accel && i > 0 && i % interval == 0) {
       k_stamp<<<1, 1, 0, st>>>(c.S, -1);
       if (w->aa.safeguard(w->v, w->v_prev, &c.S->vnorm2, &c.S->aa_rejected, &c.S->aa_accepted))
-        return failure(w, m, n, sol, info, SCS_FAILED, "error in aa_safeguard", "failure");
+        return failure(w, m_out, n, sol, info, SCS_FAILED, "error in aa_safeguard", "failure");
       k_stamp<<<1, 1, 0, st>>>(c.S, 2);
       c.launches += 2;
     }
@@ -1354,18 +1540,19 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   w->mark_begin = w->mark_end = -1;
   w->admm_iters += i;
   if (stgs->verbose) {
-    if (populate_residuals(w, i)) return failure(w, m, n, sol, info, SCS_FAILED, "error in residuals", "failure");
+    if (populate_residuals(w, i)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in residuals", "failure");
     print_summary(w, i, t0);
   }
   // ---- finalize (scs.c:874-924)
   if (!sol->x) sol->x = (double *)calloc(n, sizeof(double));
-  if (!sol->y) sol->y = (double *)calloc(m, sizeof(double));
-  if (!sol->s) sol->s = (double *)calloc(m, sizeof(double));
+  if (!sol->y) sol->y = (double *)calloc(m_out, sizeof(double));
+  if (!sol->s) sol->s = (double *)calloc(m_out, sizeof(double));
   k_finalize_sol<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->sol_x, w->sol_y, w->sol_s, w->u, w->rsk, w->D, w->E, n, m,
                                                          w->primal_scale, w->dual_scale, c.red, c.S);
   c.launches++;
-  if (populate_residuals(w, i)) return failure(w, m, n, sol, info, SCS_FAILED, "error in residuals", "failure");
-  if (c.fetch_scalars()) return failure(w, m, n, sol, info, SCS_FAILED, "fetch", "failure");
+  if (dist_finish(c, 1, 2, FinSol{})) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in finalize", "failure");
+  if (populate_residuals(w, i)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in residuals", "failure");
+  if (c.fetch_scalars()) return failure(w, m_out, n, sol, info, SCS_FAILED, "fetch", "failure");
   w->ls.tot_cg_its = c.S_host->cg_its_total;
   const double nm_s = c.S_host->fin[0], nm_y = c.S_host->fin[1], sty = c.S_host->fin[2];
   const HostResid &r = w->r_o;
@@ -1427,9 +1614,21 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   }
   k_scale3<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->sol_x, n, fx, w->sol_y, w->sol_s, m, fy, fs);
   c.launches++;
-  if (d2h(c, sol->x, w->sol_x, (size_t)n) || d2h(c, sol->y, w->sol_y, (size_t)m) || d2h(c, sol->s, w->sol_s, (size_t)m) ||
-      c.sync())
-    return failure(w, m, n, sol, info, SCS_FAILED, "solution download", "failure");
+  if (w->dist) {
+    // every rank returns the full y and s: own slice into a zeroed buffer, summed over the ranks
+    for (int which = 0; which < 2; ++which) {
+      const double *src = which == 0 ? w->sol_y : w->sol_s;
+      double *dst = which == 0 ? sol->y : sol->s;
+      if (cudaMemsetAsync(w->gather, 0, sizeof(double) * (size_t)m_out, st) != cudaSuccess ||
+          cudaMemcpyAsync(w->gather + w->row0, src, sizeof(double) * (size_t)m, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+          dist_allreduce(c, w->gather, (size_t)m_out, 0) || d2h(c, dst, w->gather, (size_t)m_out) || c.sync())
+        return failure(w, m_out, n, sol, info, SCS_FAILED, "solution gather", "failure");
+    }
+    if (d2h(c, sol->x, w->sol_x, (size_t)n) || c.sync())
+      return failure(w, m_out, n, sol, info, SCS_FAILED, "solution download", "failure");
+  } else if (d2h(c, sol->x, w->sol_x, (size_t)n) || d2h(c, sol->y, w->sol_y, (size_t)m) ||
+             d2h(c, sol->s, w->sol_s, (size_t)m) || c.sync())
+    return failure(w, m_out, n, sol, info, SCS_FAILED, "solution download", "failure");
   info->solve_time = ms_since(t0);
   info->lin_sys_time = c.S_host->phase_ns[0] * 1e-6;  // %globaltimer phase clocks, see phase_lap()
   info->cone_time = c.S_host->phase_ns[1] * 1e-6;
@@ -1454,6 +1653,22 @@ extern "C" scs_int scs(const ScsData *d, const ScsCone *k, const ScsSettings *st
   return status;
 }
 
+// Host-only view of the row partition a rank would own (used by the CPU test tier).
+extern "C" scs_int scs_b200_dist_partition(const ScsData *d, const ScsCone *k, scs_int rank, scs_int world,
+                                           scs_int out[12]) {
+  if (!d || !k || !out || !d->A || world < 1 || rank < 0 || rank >= world) return -1;
+  LocalProblem lp;
+  if (world == 1) {
+    out[0] = 0; out[1] = d->m; out[2] = d->A->p[d->n]; out[3] = k->z; out[4] = k->l; out[5] = k->bsize;
+    out[6] = k->qsize; out[7] = k->ssize; out[8] = k->cssize; out[9] = k->ep; out[10] = k->ed; out[11] = k->psize;
+    return 0;
+  }
+  if (partition_rows(d, k, rank, world, lp)) return -1;
+  out[0] = lp.row0; out[1] = lp.m; out[2] = lp.Ap[(size_t)d->n]; out[3] = lp.k.z; out[4] = lp.k.l; out[5] = lp.k.bsize;
+  out[6] = lp.k.qsize; out[7] = lp.k.ssize; out[8] = lp.k.cssize; out[9] = lp.k.ep; out[10] = lp.k.ed; out[11] = lp.k.psize;
+  return 0;
+}
+
 // ------------------------------------------------------------------ measurement -------
 extern "C" scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out) {
   if (!w || !out) return -1;
@@ -1465,6 +1680,8 @@ extern "C" scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out) {
   out->algorithmic_bytes = model_bytes(w, w->admm_iters, w->ls.tot_cg_its, w->n_checks, w->n_aa);
   out->h2d_bytes = w->c.h2d;
   out->d2h_bytes = w->c.d2h;
+  out->collectives = w->c.collectives;
+  out->collective_bytes = w->c.collective_bytes;
   return 0;
 }
 

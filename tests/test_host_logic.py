@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 import scipy.sparse as sp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -94,3 +95,73 @@ def test_bench_reference_arm_runs_on_cpu():
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert out["impl"] == "reference" and out["metric"] == "admm_iters_per_sec" and out["value"] > 0
     assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+# ------------------------------------------------------------------ row partition (dist) --
+def _partitions(data, K, world):
+    from scs_python_b200 import _scs_b200 as B
+    A = data["A"]
+    return [B.dist_partition(A.shape, A.data, A.indices, A.indptr, data["b"], data["c"], K, r, world) for r in range(world)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_row_partition_is_cone_aligned_and_balanced(world):
+    """The blocks tile [0, m), never split a second-order / exponential cone, carry every cone
+    exactly once and hold about the same number of non-zeros."""
+    from scs_python_b200 import problems as P
+    data, K, _ = P.random_cone_qp(seed=3, n=300, l=400, nq=40, q=7, ep=30, density=0.05)
+    parts = _partitions(data, K, world)
+    m, nnz = data["A"].shape[0], data["A"].nnz
+    assert parts[0]["row0"] == 0 and sum(p["m"] for p in parts) == m
+    for a, b in zip(parts[:-1], parts[1:]):
+        assert a["row0"] + a["m"] == b["row0"]
+    assert sum(p["nnz"] for p in parts) == nnz
+    assert sum(p["l"] for p in parts) == K["l"] and sum(p["qsize"] for p in parts) == len(K["q"])
+    assert sum(p["ep"] for p in parts) == K["ep"]
+    for p in parts:  # rows of a block = rows of the cones it holds
+        assert p["m"] == p["z"] + p["l"] + 7 * p["qsize"] + 3 * p["ep"]
+        assert p["nnz"] <= nnz / world * 1.25 + 50
+
+
+def test_row_partition_lasso_and_errors():
+    from scs_python_b200 import problems as P
+    data, K, _ = P.lasso(500, 1000, 10, seed=0)
+    parts = _partitions(data, K, 4)
+    assert sum(p["z"] for p in parts) == K["z"] and sum(p["l"] for p in parts) == K["l"]
+    # a single PSD cone cannot be cut
+    d4, K4, _ = P.maxcut_sdp(nodes=6, blocks=1)
+    with pytest.raises(ValueError):
+        _partitions(d4, K4, 2)
+
+
+_DIST_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import torch.distributed as td
+td.init_process_group(backend="gloo")
+rank, world = td.get_rank(), td.get_world_size()
+from scs_python_b200 import _scs_b200 as B, problems as P
+data, K, _ = P.random_cone_qp(seed=5, n=120, l=200, nq=20, q=5, ep=10, density=0.1)
+A = data["A"]
+mine = B.dist_partition(A.shape, A.data, A.indices, A.indptr, data["b"], data["c"], K, rank, world)
+box = [None] * world
+td.all_gather_object(box, mine)
+if rank == 0:
+    print(json.dumps(dict(world=world, parts=box, m=int(A.shape[0]))))
+td.barrier()
+td.destroy_process_group()
+'''
+
+
+def test_row_partition_world_size_2_gloo(tmp_path):
+    """Two processes (gloo) each derive their own block from the full problem, as the ranks of a
+    row-partitioned solve do; together the blocks tile the rows."""
+    script = tmp_path / "dist_worker.py"
+    script.write_text(_DIST_WORKER % dict(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29641", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    p0, p1 = out["parts"]
+    assert out["world"] == 2 and p0["row0"] == 0 and p0["m"] == p1["row0"] and p0["m"] + p1["m"] == out["m"]
