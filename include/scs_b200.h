@@ -280,12 +280,23 @@ scs_int scs_b200_dist_partition(const ScsData *d, const ScsCone *k, scs_int rank
 scs_int scs_b200_dist_rank(void);
 scs_int scs_b200_dist_world(void);
 
-/* Solve `count` independent problems on the current device, one after another on
- * `streams` concurrent streams (batch sharding across GPUs is done by the caller: one
- * process per GPU, problem i -> rank i % world).  Arrays of pointers, one per problem. */
+/* Solve `count` independent problems on the current device (no reference counterpart: the
+ * reference API is single-problem; BASELINE.json configs[4]).  Arrays of pointers,
+ * one per problem; `sol[i]` vectors are allocated when NULL, exactly as scs_solve does.  Problems
+ * that fit (zero / nonneg / second-order cones, shared-memory footprint <= 200 KB, cold start,
+ * lookback <= 10) are solved by the batch engine: ONE kernel launch, one CTA per problem with all
+ * state in shared memory (csrc/batch.cu); the others go through the streaming engine one after
+ * another.  Batch sharding across GPUs is done by the caller: one process per GPU, problem
+ * i -> rank i % world, no collective.  `streams` is reserved.  Returns 0, or the worst failure code. */
 scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, const ScsCone *const *k,
                              const ScsSettings *stgs, ScsSolution *const *sol, ScsInfo *info,
                              scs_int streams);
+/* how the last scs_b200_solve_batch of this process ran: out = {problems in the batch engine,
+ * problems streamed, batch-kernel ms (CUDA events), host packing ms, H2D bytes, D2H bytes,
+ * CTAs launched, shared memory per CTA, 1 if the batch kernel ran in direct mode (resident dense
+ * inverse) / 0 for PCG, total CG iterations, total ADMM iterations, 0, then SM cycles summed over the
+ * problems: equilibration, factorisation, linear solves, Anderson acceleration, residual checks, total} */
+scs_int scs_b200_batch_stats(double out[18]);
 
 #ifdef __cplusplus
 }

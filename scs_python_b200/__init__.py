@@ -69,51 +69,57 @@ def _has_lower_tri(P):
     return bool(np.any(last_row > np.where(nonempty)[0]))
 
 
+def _prepare(data, cone):
+    """Validation and CSC / upper-triangle conversion of scs.SCS.__init__ (scs/py/__init__.py:89-184);
+    returns the positional arguments of the extension type's constructor."""
+    if not data or not cone:
+        raise ValueError("Missing data or cone information")
+    if "b" not in data or "c" not in data:
+        raise ValueError("Missing one of b, c from data dictionary")
+    if "A" not in data:
+        raise ValueError("Missing A from data dictionary")
+    A, b, c = data["A"], data["b"], data["c"]
+    if A is None or b is None or c is None:
+        raise ValueError("Incomplete data specification")
+    if not sparse.issparse(A):
+        raise TypeError("A is required to be a sparse matrix")
+    if not A.format == "csc":
+        warnings.warn("Converting A to a CSC (compressed sparse column) matrix; may take a while.")
+        A = A.tocsc()
+    if sparse.issparse(b):
+        b = np.asarray(b.todense()).ravel()
+    if sparse.issparse(c):
+        c = np.asarray(c.todense()).ravel()
+    m, n = len(b), len(c)
+    if not A.has_sorted_indices:
+        A = A.sorted_indices()
+    if A.shape != (m, n):
+        raise ValueError("A shape not compatible with b,c")
+    Pdata = Pindices = Pcolptr = None
+    P = data.get("P", None)
+    if P is not None:
+        if not sparse.issparse(P):
+            raise TypeError("P is required to be a sparse matrix")
+        if P.shape != (n, n):
+            raise ValueError("P shape not compatible with A,b,c")
+        if not P.format == "csc":
+            warnings.warn("Converting P to a CSC (compressed sparse column) matrix; may take a while.")
+            P = P.tocsc()
+        if not P.has_sorted_indices:
+            P = P.sorted_indices()
+        if _has_lower_tri(P):
+            P = sparse.triu(P, format="csc")
+        Pdata, Pindices, Pcolptr = P.data, P.indices, P.indptr
+    return ((m, n), A.data, A.indices, A.indptr, Pdata, Pindices, Pcolptr, np.asarray(b), np.asarray(c), cone)
+
+
 class SCS(object):
     def __init__(self, data, cone, **settings):
         """Same contract as scs.SCS.__init__ (scs/py/__init__.py:89-184)."""
         self._settings = settings
-        if not data or not cone:
-            raise ValueError("Missing data or cone information")
-        if "b" not in data or "c" not in data:
-            raise ValueError("Missing one of b, c from data dictionary")
-        if "A" not in data:
-            raise ValueError("Missing A from data dictionary")
-        A, b, c = data["A"], data["b"], data["c"]
-        if A is None or b is None or c is None:
-            raise ValueError("Incomplete data specification")
-        if not sparse.issparse(A):
-            raise TypeError("A is required to be a sparse matrix")
-        if not A.format == "csc":
-            warnings.warn("Converting A to a CSC (compressed sparse column) matrix; may take a while.")
-            A = A.tocsc()
-        if sparse.issparse(b):
-            b = np.asarray(b.todense()).ravel()
-        if sparse.issparse(c):
-            c = np.asarray(c.todense()).ravel()
-        m, n = len(b), len(c)
-        if not A.has_sorted_indices:
-            A = A.sorted_indices()
-        if A.shape != (m, n):
-            raise ValueError("A shape not compatible with b,c")
-        Pdata = Pindices = Pcolptr = None
-        P = data.get("P", None)
-        if P is not None:
-            if not sparse.issparse(P):
-                raise TypeError("P is required to be a sparse matrix")
-            if P.shape != (n, n):
-                raise ValueError("P shape not compatible with A,b,c")
-            if not P.format == "csc":
-                warnings.warn("Converting P to a CSC (compressed sparse column) matrix; may take a while.")
-                P = P.tocsc()
-            if not P.has_sorted_indices:
-                P = P.sorted_indices()
-            if _has_lower_tri(P):
-                P = sparse.triu(P, format="csc")
-            Pdata, Pindices, Pcolptr = P.data, P.indices, P.indptr
+        args = _prepare(data, cone)
         _scs = _select_scs_module(self._settings)
-        self._solver = _scs.SCS((m, n), A.data, A.indices, A.indptr, Pdata, Pindices, Pcolptr,
-                                np.asarray(b), np.asarray(c), cone, **self._settings)
+        self._solver = _scs.SCS(*args, **self._settings)
 
     def solve(self, warm_start=True, x=None, y=None, s=None):
         """scs/py/__init__.py:186-203."""
@@ -146,6 +152,20 @@ def dist_init(rank=None, world=None):
 
 def dist_finalize():
     _load_b200().dist_finalize()
+
+
+def solve_batch(problems, **settings):
+    """Solve independent problems in one call: `problems` is a sequence of (data, cone) pairs with
+    the meaning `SCS(data, cone)` gives them; every problem uses the same settings and a cold start.
+    Small problems with zero / nonneg / second-order cones run in the batch engine (one CTA per
+    problem, one kernel launch for the whole batch; BASELINE.json configs[4]); anything else is
+    solved by the streaming engine one after another.  The reference API is single-problem
+    (scs/py/__init__.py:89-230), so this entry point has no reference counterpart; each result is
+    what `SCS(data, cone, **settings).solve(warm_start=False)` returns.  Shard a batch across GPUs by
+    giving rank r the problems r, r + world, ... (no communication)."""
+    settings = dict(settings)
+    _scs = _select_scs_module(settings)
+    return _scs.solve_batch([_prepare(d, k) for d, k in problems], **settings)
 
 
 def solve(data, cone, **settings):

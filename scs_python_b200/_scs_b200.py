@@ -161,6 +161,12 @@ lib.scs_b200_get_marks.restype = c_int
 lib.scs_b200_get_marks.argtypes = [C.c_void_p, C.POINTER(ScsB200Marks)]
 lib.scs_b200_bench_spmv.restype = c_double
 lib.scs_b200_bench_spmv.argtypes = [C.c_void_p, c_int, c_int, p_double]
+lib.scs_b200_solve_batch.restype = c_int
+lib.scs_b200_solve_batch.argtypes = [c_int, C.POINTER(C.POINTER(ScsData)), C.POINTER(C.POINTER(ScsCone)),
+                                     C.POINTER(ScsSettings), C.POINTER(C.POINTER(ScsSolution)),
+                                     C.POINTER(ScsInfo), c_int]
+lib.scs_b200_batch_stats.restype = c_int
+lib.scs_b200_batch_stats.argtypes = [C.POINTER(c_double * 18)]
 
 
 def dist_unique_id():
@@ -387,6 +393,67 @@ _AA_KEYS = ("iter", "n_accept", "n_reject_lapack", "n_reject_rank0", "n_reject_n
             "n_reject_weight_cap", "n_safeguard_reject", "last_rank", "last_aa_norm", "last_regularization")
 
 
+def _info_dict(info):
+    d = {key: getattr(info, key) for key in _INFO_KEYS}
+    d["status"] = info.status.decode()
+    d["lin_sys_solver"] = info.lin_sys_solver.decode()
+    d["aa_stats"] = {key: getattr(info.aa_stats, key) for key in _AA_KEYS}
+    return d
+
+
+def solve_batch(problems, **settings):
+    """Solve independent problems in one call (include/scs_b200.h: scs_b200_solve_batch).
+
+    problems: sequence of (shape, Ax, Ai, Ap, Px, Pi, Pp, b, c, cone) tuples -- the constructor
+    arguments of `SCS` -- all solved with the same settings.  Returns a list of
+    {"x","y","s","info"} dicts in input order."""
+    cnt = len(problems)
+    stgs, keep_stgs = make_settings(settings)
+    keep = []
+    datas = (C.POINTER(ScsData) * max(cnt, 1))()
+    cones = (C.POINTER(ScsCone) * max(cnt, 1))()
+    sols = (C.POINTER(ScsSolution) * max(cnt, 1))()
+    infos = (ScsInfo * max(cnt, 1))()
+    out = []
+    for idx, (shape, Ax, Ai, Ap, Px, Pi, Pp, b, c, cone) in enumerate(problems):
+        m, n = int(shape[0]), int(shape[1])
+        if m <= 0 or n <= 0:
+            raise ValueError("m and n must be positive integers")
+        if not isinstance(cone, dict):
+            raise TypeError("cone must be a dict")
+        Ax = _check_float_1d(Ax, "Ax"); Ai = _check_int_1d(Ai, "Ai"); Ap = _check_int_1d(Ap, "Ap")
+        if len(Ap) != n + 1:
+            raise ValueError("Ap has incompatible dimension with A")
+        A = make_matrix(Ax, Ai, Ap, m, n)
+        P = None
+        if Px is not None and Pi is not None and Pp is not None:
+            Px = _check_float_1d(Px, "Px"); Pi = _check_int_1d(Pi, "Pi"); Pp = _check_int_1d(Pp, "Pp")
+            P = make_matrix(Px, Pi, Pp, n, n)
+        c = _check_float_1d(c, "c"); b = _check_float_1d(b, "b")
+        if c.shape[0] != n:
+            raise ValueError("c has incompatible dimension with A")
+        if b.shape[0] != m:
+            raise ValueError("b has incompatible dimension with A")
+        k, keep_cone = make_cone(cone)
+        d = ScsData(m, n, C.pointer(A), C.pointer(P) if P is not None else None, _dptr(b), _dptr(c))
+        x, y, s = np.zeros(n), np.zeros(m), np.zeros(m)
+        sol = ScsSolution(_dptr(x), _dptr(y), _dptr(s))
+        keep.append((Ax, Ai, Ap, Px, Pi, Pp, b, c, A, P, k, keep_cone, d, sol))
+        datas[idx] = C.pointer(d); cones[idx] = C.pointer(k); sols[idx] = C.pointer(sol)
+        out.append((x, y, s))
+    lib.scs_b200_solve_batch(cnt, datas, cones, C.byref(stgs), sols, infos, 0)  # ctypes releases the GIL
+    del keep_stgs
+    return [{"x": x, "y": y, "s": s, "info": _info_dict(infos[i])} for i, (x, y, s) in enumerate(out)]
+
+
+def batch_stats():
+    buf = (c_double * 18)()
+    lib.scs_b200_batch_stats(C.byref(buf))
+    keys = ("fused", "streamed", "kernel_ms", "pack_ms", "h2d_bytes", "d2h_bytes", "ctas", "smem_per_cta", "direct",
+            "cg_iters", "admm_iters", "_", "clk_equil", "clk_factor", "clk_linsys", "clk_aa", "clk_resid", "clk_total")
+    return dict(zip(keys, list(buf)))
+
+
 class SCS(object):
     """Same constructor / methods as the extension type `scs.SCS` (scsobject.h:1261-1307)."""
 
@@ -450,11 +517,7 @@ class SCS(object):
             info = ScsInfo()
             lib.scs_solve(self._work, C.byref(self._sol), C.byref(info), 1 if warm_start else 0)
             out_x, out_y, out_s = self._x.copy(), self._y.copy(), self._s.copy()
-        info_dict = {key: getattr(info, key) for key in _INFO_KEYS}
-        info_dict["status"] = info.status.decode()
-        info_dict["lin_sys_solver"] = info.lin_sys_solver.decode()
-        info_dict["aa_stats"] = {key: getattr(info.aa_stats, key) for key in _AA_KEYS}
-        return {"x": out_x, "y": out_y, "s": out_s, "info": info_dict}
+        return {"x": out_x, "y": out_y, "s": out_s, "info": _info_dict(info)}
 
     def update(self, b, c):
         bb = cc = None

@@ -560,7 +560,7 @@ static inline double ms_since(const Clock::time_point &t0) {
 }
 
 // ------------------------------------------------------------------ validation --------
-static int validate(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {  // scs.c:364-429
+int validate_problem(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {  // scs.c:364-429
   if (d->m <= 0 || d->n <= 0) {
     B200_PRINTF("m and n must both be greater than 0; m = %li, n = %li\n", (long)d->m, (long)d->n);
     return -1;
@@ -1105,7 +1105,7 @@ static void free_work(SCS_WORK *w) {
 }
 
 // populate_on_failure / failure, scs.c:316-359
-static void populate_on_failure(int m, int n, ScsSolution *sol, ScsInfo *info, int status_val, const char *msg) {
+void populate_on_failure(int m, int n, ScsSolution *sol, ScsInfo *info, int status_val, const char *msg) {
   if (info) {
     info->gap = NAN; info->res_pri = NAN; info->res_dual = NAN; info->pobj = NAN; info->dobj = NAN;
     info->iter = -1; info->status_val = status_val; info->solve_time = NAN;
@@ -1325,7 +1325,7 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
     B200_PRINTF("ERROR: Missing ScsData, ScsCone, or ScsSettings input\n");
     return nullptr;
   }
-  if (validate(d, k, stgs) < 0) {
+  if (validate_problem(d, k, stgs) < 0) {
     B200_PRINTF("ERROR: Validation returned failure\n");
     return nullptr;
   }
@@ -1731,17 +1731,4 @@ extern "C" double scs_b200_bench_spmv(ScsWork *w, scs_int which, scs_int reps, d
   cudaEventDestroy(e1);
   if (alg_bytes) *alg_bytes = which == 0 ? ls.bytes_A() : (ls.bytes_At() + ls.bytes_P());
   return (double)ms / reps;
-}
-
-extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, const ScsCone *const *k,
-                                        const ScsSettings *stgs, ScsSolution *const *sol, ScsInfo *info,
-                                        scs_int streams) {
-  (void)streams;
-  if (count < 0 || !d || !k || !stgs || !sol || !info) return -1;
-  scs_int worst = 0;
-  for (scs_int i = 0; i < count; ++i) {
-    const scs_int st = scs(d[i], k[i], stgs, sol[i], &info[i]);
-    if (st < 0 && st != SCS_INFEASIBLE && st != SCS_UNBOUNDED) worst = st;
-  }
-  return worst;
 }

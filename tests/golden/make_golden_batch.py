@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Generate tests/golden/batch_ref.json: outputs of the compiled reference (oracle/_ref, built from
+/root/reference by `make -C oracle ref`) on the seeded small problems the batch engine is checked on.
+Runs ONLY in the build container; the fixture is committed.
+
+    make -C oracle ref && python tests/golden/make_golden_batch.py
+
+Cases: BASELINE.json configs[4] MPC QPs (scs_python_b200.problems.mpc_qp, seeds 0..23) and small
+second-order-cone programs (tests/problems.gen_feasible), each solved by scs.SCS(...).solve() with
+QDLDL and CPU_INDIRECT at eps 1e-4 (defaults) and 1e-9.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+
+import numpy as np  # noqa: E402
+
+
+def rec_of(sol):
+    i = sol["info"]
+    f = lambda v: ("nan" if v != v else ("inf" if v == float("inf") else ("-inf" if v == float("-inf") else float(v))))
+    return dict(status=i["status"], status_val=int(i["status_val"]), iter=int(i["iter"]), pobj=f(i["pobj"]), dobj=f(i["dobj"]),
+                res_pri=f(i["res_pri"]), res_dual=f(i["res_dual"]), gap=f(i["gap"]), scale_updates=int(i["scale_updates"]))
+
+
+def main():
+    if not os.path.isdir("/root/reference"):
+        sys.exit("make_golden_batch.py needs /root/reference (build container only)")
+    import scs
+    from scs_python_b200 import problems as bp
+    from tests import problems as tp
+    out = dict(source="scs.SCS(...).solve() of oracle/_ref (SCS 3.2.11), QDLDL and CPU_INDIRECT", mpc=[], soc=[])
+    for seed in range(24):
+        data, cone, _ = bp.mpc_qp(seed)
+        rec = dict(seed=seed, runs={})
+        for eps in (1e-4, 1e-9):
+            for name, ls in (("qdldl", scs.LinearSolver.QDLDL), ("cpu_indirect", scs.LinearSolver.CPU_INDIRECT)):
+                sol = scs.SCS(data, cone, linear_solver=ls, verbose=False, eps_abs=eps, eps_rel=eps, max_iters=100000).solve()
+                rec["runs"]["%s_%g" % (name, eps)] = rec_of(sol)
+        out["mpc"].append(rec)
+    for seed, K, n, withP in [(3, dict(z=4, l=10, q=[3, 5, 8]), 20, True), (4, dict(z=0, l=30, q=[4] * 10 + [1, 2]), 35, False),
+                              (5, dict(z=6, l=0, q=[12, 40]), 30, True), (6, dict(z=2, l=50), 25, True)]:
+        data, p_star = tp.gen_feasible(K, n, 0.3, seed, with_P=withP)
+        rec = dict(seed=seed, cone=K, n=n, with_P=withP, p_star=p_star, runs={})
+        for eps in (1e-4, 1e-9):
+            for name, ls in (("qdldl", scs.LinearSolver.QDLDL), ("cpu_indirect", scs.LinearSolver.CPU_INDIRECT)):
+                sol = scs.SCS(data, K, linear_solver=ls, verbose=False, eps_abs=eps, eps_rel=eps, max_iters=100000).solve()
+                rec["runs"]["%s_%g" % (name, eps)] = rec_of(sol)
+        out["soc"].append(rec)
+    json.dump(out, open(os.path.join(HERE, "batch_ref.json"), "w"), indent=0)
+    its = [r["runs"]["cpu_indirect_0.0001"]["iter"] for r in out["mpc"]]
+    print("batch_ref.json: %d mpc, %d soc; mpc iters at 1e-4 (indirect): min %d median %d max %d" %
+          (len(out["mpc"]), len(out["soc"]), min(its), int(np.median(its)), max(its)))
+    print([(r["runs"]["qdldl_0.0001"]["iter"], r["runs"]["cpu_indirect_1e-09"]["iter"], r["runs"]["cpu_indirect_1e-09"]["status"]) for r in out["mpc"]][:8])
+
+
+if __name__ == "__main__":
+    main()
