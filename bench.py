@@ -341,8 +341,15 @@ def run_b200(args):
         a_ms = mk["spmv_a_ms"] / max(1, mk["spmv_a_launches"])
         ach = mk["bytes_g"] / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
         nnz_g = desc["nnz_A"] + desc["nnz_P"]
+        eng = solver._solver.stats()
+        tiled = bool(eng.get("tiled_g"))
+        k_g = ("tiled_kernel<EpiG> (2-D tiled, x-slices by TMA into shared memory, y in shared memory)" if tiled
+               else "row_kernel<ElemMul,ElemMul,EpiG,DUAL>")
+        k_a = ("tiled_kernel<EpiScaleRy>" if eng.get("tiled_a") else "row_kernel<ElemMul,ElemMul,EpiScaleRy>")
         roofline = dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=ncu_traffic(),
-                        kernel="row_kernel<ElemMul,ElemMul,EpiG,DUAL> (Gp = A' z + P p + R_x p, p'Gp fused)",
+                        kernel=k_g + " (Gp = A' z + P p + R_x p, p'Gp fused)",
+                        engine=dict(tiled_a=int(eng.get("tiled_a", 0)), tiled_g=int(eng.get("tiled_g", 0)),
+                                    stored_slots_per_nnz=(eng["tiled_slots"] / eng["tiled_nnz"] if eng.get("tiled_nnz") else None)),
                         avg_launch_ms=g_ms, launches_timed=int(mk["spmv_g_launches"]),
                         timing="device %globaltimer, first CTA start -> last CTA end, every launch inside the timed "
                                "region (graph WHILE-body launches cannot carry CUDA events)",
@@ -353,7 +360,7 @@ def run_b200(args):
                         gather_ceiling_frac=(nnz_g / (g_ms * 1e-3) / 1e9 / GATHER_CEILING_GELEMS if g_ms > 0 else 0.0),
                         gather_note="one random FP64 operand per stored non-zero: 32 B L2 sector per 8 B; measured "
                                     "ceiling 272 G gathers/s on B200 (profiles/r1b_gather_probe_*.txt, DESIGN.md 3.1)",
-                        second_kernel=dict(kernel="row_kernel<ElemMul,ElemMul,EpiScaleRy> (z = R_y^-1 A p)",
+                        second_kernel=dict(kernel=k_a + " (z = R_y^-1 A p)",
                                            avg_launch_ms=a_ms, launches_timed=int(mk["spmv_a_launches"]),
                                            isolated_event_ms=iso_a_ms,
                                            achieved=(mk["bytes_a"] / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0)),

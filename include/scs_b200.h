@@ -240,6 +240,10 @@ typedef struct {
   long long d2h_bytes;        /* bytes copied device->host by this workspace */
   long long collectives;      /* NCCL all-reduces issued (row-partitioned mode) */
   long long collective_bytes; /* bytes all-reduced */
+  long long tiled_a;          /* 1 when A x runs on the tiled shared-memory SpMV engine (csrc/tiled.cuh) */
+  long long tiled_g;          /* 1 when A'z + P p runs on it */
+  long long tiled_slots;      /* stored slots of both tiled operators, padding included */
+  long long tiled_nnz;        /* non-zeros they hold */
 } ScsB200Stats;
 scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out);
 
@@ -248,6 +252,11 @@ scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out);
  * Runs `reps` launches on the workspace's stream, returns average ms per launch measured
  * with CUDA events on that stream; *alg_bytes gets the algorithmic bytes of one launch. */
 double scs_b200_bench_spmv(ScsWork *w, scs_int which, scs_int reps, double *alg_bytes);
+
+/* Per-CTA profile of the last launch of a tiled operator (which = 0: A, 1: [A' | P]): 4 doubles per CTA
+ * = duration in us, us spent streaming non-zeros, modelled cost of its item list, items.  Returns the CTA
+ * count (0 when the operator runs on the row engine). */
+scs_int scs_b200_tiled_profile(ScsWork *w, scs_int which, double *out, scs_int cap);
 
 /* Iteration marks: the next scs_solve records a CUDA event on the workspace stream at the
  * top of ADMM iteration `begin_iter` and of `end_iter` (or at loop exit if earlier), and

@@ -85,7 +85,9 @@ class ScsB200Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_longlong), ("cg_iters", C.c_longlong), ("admm_iters", C.c_longlong),
                 ("spmv_calls", C.c_longlong), ("spmv_ms", c_double), ("algorithmic_bytes", c_double),
                 ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
-                ("collectives", C.c_longlong), ("collective_bytes", C.c_longlong)]
+                ("collectives", C.c_longlong), ("collective_bytes", C.c_longlong),
+                ("tiled_a", C.c_longlong), ("tiled_g", C.c_longlong), ("tiled_slots", C.c_longlong),
+                ("tiled_nnz", C.c_longlong)]
 
 
 class ScsB200Marks(C.Structure):
@@ -161,6 +163,8 @@ lib.scs_b200_get_marks.restype = c_int
 lib.scs_b200_get_marks.argtypes = [C.c_void_p, C.POINTER(ScsB200Marks)]
 lib.scs_b200_bench_spmv.restype = c_double
 lib.scs_b200_bench_spmv.argtypes = [C.c_void_p, c_int, c_int, p_double]
+lib.scs_b200_tiled_profile.restype = c_int
+lib.scs_b200_tiled_profile.argtypes = [C.c_void_p, c_int, p_double, c_int]
 lib.scs_b200_solve_batch.restype = c_int
 lib.scs_b200_solve_batch.argtypes = [c_int, C.POINTER(C.POINTER(ScsData)), C.POINTER(C.POINTER(ScsCone)),
                                      C.POINTER(ScsSettings), C.POINTER(C.POINTER(ScsSolution)),
@@ -564,6 +568,12 @@ class SCS(object):
         with self._lock:
             ms = lib.scs_b200_bench_spmv(self._work, int(which), int(reps), C.byref(ab))
         return ms, ab.value
+
+    def tiled_profile(self, which):
+        buf = np.zeros(4 * 1024)
+        with self._lock:
+            n = lib.scs_b200_tiled_profile(self._work, int(which), _dptr(buf), 1024)
+        return buf[:4 * max(n, 0)].reshape(-1, 4)
 
     def finish(self):
         with self._lock:

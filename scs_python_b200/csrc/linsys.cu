@@ -23,9 +23,14 @@ struct EpiScaleRy {
   double *out;
   const double *ry;  // diag_r + n
   DevScalars *S_;
+  int kt_cont = 0;   // 1: the timing window was opened by the streaming kernel of tiled_launch
   __device__ __forceinline__ void row2(State &, int, double, double) const {}
-  __device__ __forceinline__ void init(State &) const { kt_begin(S_, 0); }
+  __device__ __forceinline__ void init(State &) const { if (!kt_cont) kt_begin(S_, 0); }
   __device__ __forceinline__ void row(State &, int i, double acc) const { out[i] = acc / ry[i]; }
+  // two-stage form used by tiled_epilogue_kernel: all global loads of a batch of rows first, then the stores
+  struct Pre { double ry; };
+  __device__ __forceinline__ Pre load(int i) const { return Pre{ry[i]}; }
+  __device__ __forceinline__ void apply(State &, int i, double acc, const Pre &q) const { out[i] = acc / q.ry; }
   __device__ __forceinline__ void finish(State &, const RedWs &, DevScalars *S) const { kt_end_ticket(S, 0); }
 };
 // Gp_j = (A' z)_j + (P p)_j + R_x,j p_j ; p'Gp ; alpha = z'r / p'Gp     (private.c:181-183)
@@ -37,13 +42,21 @@ struct EpiG {
   const double *p, *rx;
   DevScalars *S_;
   const double *extra;  // row-partitioned mode: all-reduced A'z (acc then only holds P p), else null
-  __device__ __forceinline__ void init(State &s) const { s.pgp = 0.0; kt_begin(S_, 1); }
+  int kt_cont = 0;      // 1: the timing window was opened by the streaming kernel of tiled_launch
+  __device__ __forceinline__ void init(State &s) const { s.pgp = 0.0; if (!kt_cont) kt_begin(S_, 1); }
   __device__ __forceinline__ void row(State &s, int j, double acc) const {
     const double pj = p[j];
     if (extra) acc += extra[j];
     const double g = acc + rx[j] * pj;
     Gp[j] = g;
     s.pgp = fma(pj, g, s.pgp);
+  }
+  struct Pre { double p, rx; };
+  __device__ __forceinline__ Pre load(int j) const { return Pre{p[j], rx[j]}; }
+  __device__ __forceinline__ void apply(State &s, int j, double acc, const Pre &q) const {  // == row(), extra == null
+    const double g = acc + q.rx * q.p;
+    Gp[j] = g;
+    s.pgp = fma(q.p, g, s.pgp);
   }
   __device__ __forceinline__ void finish(State &s, const RedWs &ws, DevScalars *S) const {
     double v[1] = {s.pgp};
@@ -65,6 +78,7 @@ struct EpiG0 {
   double *r, *z, *p;
   CgCtl ctl;
   const double *extra;  // row-partitioned mode: all-reduced A' R_y^-1 A s (may alias r), else null
+  int kt_cont = 0;      // (set by tiled_launch; this epilogue carries no timing hooks)
   __device__ __forceinline__ void init(State &st) const { st.ztr = 0.0; st.nr = 0.0; }
   __device__ __forceinline__ void row(State &st, int j, double acc) const {
     const double sj = s[j];
@@ -72,6 +86,18 @@ struct EpiG0 {
     const double rj = b[j] - (acc + rx[j] * sj);
     const double zj = rj * M[j];
     b[j] = sj;
+    r[j] = rj;
+    z[j] = zj;
+    p[j] = zj;
+    st.ztr = fma(zj, rj, st.ztr);
+    st.nr = fmax(st.nr, fabs(rj));
+  }
+  struct Pre { double b, s, rx, M; };
+  __device__ __forceinline__ Pre load(int j) const { return Pre{b[j], s[j], rx[j], M[j]}; }
+  __device__ __forceinline__ void apply(State &st, int j, double acc, const Pre &q) const {  // == row(), extra == null
+    const double rj = q.b - (acc + q.rx * q.s);
+    const double zj = rj * q.M;
+    b[j] = q.s;
     r[j] = rj;
     z[j] = zj;
     p[j] = zj;
@@ -94,7 +120,11 @@ struct EpiG0 {
 struct EpiY : EpiNoState {
   double *by;        // b + n
   const double *ry;  // diag_r + n
+  int kt_cont = 0;   // (set by tiled_launch; this epilogue carries no timing hooks)
   __device__ __forceinline__ void row(State &, int i, double acc) const { by[i] = (acc - by[i]) / ry[i]; }
+  struct Pre { double by, ry; };
+  __device__ __forceinline__ Pre load(int i) const { return Pre{by[i], ry[i]}; }
+  __device__ __forceinline__ void apply(State &, int i, double acc, const Pre &q) const { by[i] = (acc - q.by) / q.ry; }
 };
 // M_j = 1 / (R_x,j + sum_k A_kj^2 / R_y,k + P_jj)        (private.c:60-80)
 struct EpiPrecond : EpiNoState {
@@ -258,7 +288,16 @@ int LinSys::init(Ctx *ctx, const ScsMatrix *Ah, const ScsMatrix *Ph) {
   return 0;
 }
 
-int LinSys::finalize_structure() { return 0; }
+int LinSys::finalize_structure() {
+  tA.destroy();
+  tG.destroy();
+  const int mode = tiled_env_mode();  // SCS_B200_TILED: 0 never, 1 force, unset: heuristic
+  if (mode == 0 || c->dist) return 0;
+  if (tiled_prepare()) return -1;
+  if (tA.build(*c, A, nullptr, mode == 1)) return -1;
+  if (tG.build(*c, At, hasP ? &P : nullptr, mode == 1)) return -1;
+  return 0;
+}
 
 void LinSys::destroy() {
   if (!c) return;
@@ -266,6 +305,8 @@ void LinSys::destroy() {
   csr_free(A);
   csr_free(At);
   csr_free(P);
+  tA.destroy();
+  tG.destroy();
   chunks_free(chA);
   chunks_free(chAt);
   chunks_free(chP);
@@ -315,9 +356,13 @@ int LinSys::launch_A_scaled(const double *x, double *out, const int *skip, int t
   epi.out = out; epi.ry = diag_r + n; epi.S_ = c->S;
   ElemMul e{x};
   (void)tag;
-  row_kernel<ElemMul, ElemMul, EpiScaleRy, false>
-      <<<chA.grid, kThreads, 0, c->stream>>>(A, e, A, e, chA.d, chA.n, epi, c->red, c->S, skip);
-  if (counted) { c->launches++; c->spmv_calls++; }
+  int nl = 1;
+  if (tA.ok && tiled_aligned(x)) {
+    nl = tiled_launch(tA, x, nullptr, epi, *c, skip, 0);
+  } else
+    row_kernel<ElemMul, ElemMul, EpiScaleRy, false>
+        <<<chA.grid, kThreads, 0, c->stream>>>(A, e, A, e, chA.d, chA.n, epi, c->red, c->S, skip);
+  if (counted) { c->launches += nl; c->spmv_calls++; }
   return 0;
 }
 
@@ -338,7 +383,11 @@ int LinSys::launch_G(const double *zin, const double *pin, double *out, const in
     if (counted) { c->launches += 2; c->spmv_calls += 2; }
     return 0;
   }
-  if (hasP)
+  if (tG.ok && tiled_aligned(zin) && tiled_aligned(pin)) {
+    const int nl = tiled_launch(tG, zin, pin, epi, *c, skip, 1);
+    if (counted) { c->launches += nl; c->spmv_calls++; }
+    return 0;
+  } else if (hasP)
     row_kernel<ElemMul, ElemMul, EpiG, true>
         <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, P, eb, chAt.d, chAt.n, epi, c->red, c->S, skip);
   else
@@ -392,7 +441,9 @@ int LinSys::enqueue_head(double *b, const double *ws, CgCtl ctl) {
       row_kernel<ElemMul, ElemMul, EpiG0, false>
           <<<chP.grid, kThreads, 0, st>>>(P, eb, P, eb, chP.d, chP.n, epi, cx.red, S, done);
       cx.launches++;
-    } else if (hasP)
+    } else if (tG.ok && tiled_aligned(tmp) && tiled_aligned(ws))
+      cx.launches += tiled_launch(tG, tmp, ws, epi, cx, done) - 1;
+    else if (hasP)
       row_kernel<ElemMul, ElemMul, EpiG0, true>
           <<<chAt.grid, kThreads, 0, st>>>(At, ea, P, eb, chAt.d, chAt.n, epi, cx.red, S, done);
     else
@@ -426,8 +477,11 @@ int LinSys::enqueue_tail(double *b) {
   DevScalars *S = cx.S;
   EpiY epi; epi.by = b + n; epi.ry = diag_r + n;
   ElemMul e{b};
-  row_kernel<ElemMul, ElemMul, EpiY, false>
-      <<<chA.grid, kThreads, 0, cx.stream>>>(A, e, A, e, chA.d, chA.n, epi, cx.red, S, &S->zero_rhs);
+  if (tA.ok && tiled_aligned(b))
+    cx.launches += tiled_launch(tA, b, nullptr, epi, cx, &S->zero_rhs) - 1;
+  else
+    row_kernel<ElemMul, ElemMul, EpiY, false>
+        <<<chA.grid, kThreads, 0, cx.stream>>>(A, e, A, e, chA.d, chA.n, epi, cx.red, S, &S->zero_rhs);
   k_zero_if<<<ew_grid(cx, n + m), kThreads, 0, cx.stream>>>(b, n + m, &S->zero_rhs);
   cx.launches += 2; cx.spmv_calls++;
   return 0;
@@ -492,7 +546,7 @@ extern "C" const char *scs_get_lin_sys_method(void) { return "sparse-indirect-b2
 extern "C" ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P, const scs_float *diag_r) {
   if (!A || !diag_r) return nullptr;
   SCS_LIN_SYS_WORK *w = new SCS_LIN_SYS_WORK();
-  if (w->ctx.init(g_device) || w->ls.init(&w->ctx, A, P)) {
+  if (w->ctx.init(g_device) || w->ls.init(&w->ctx, A, P) || w->ls.finalize_structure()) {
     scs_free_lin_sys_work(w);
     return nullptr;
   }

@@ -11,6 +11,7 @@
 // of enqueued CG iterations.
 #pragma once
 #include "sparse.cuh"
+#include "tiled.cuh"
 
 namespace b200 {
 
@@ -31,6 +32,9 @@ struct LinSys {
   // (p'Gp, z'r, x'Px ...) -- is identical on all ranks, which keeps the CG scalars and hence
   // the ranks' control flow bit-identical.
   ChunkList chP;
+  // tiled shared-memory format (tiled.cuh) of CSR(A) and of [CSR(A') | CSR(P)], built by
+  // finalize_structure() for large matrices; the CG-loop products go through it when present
+  TiledOp tA, tG;
   double *diag_r = nullptr;  // n+m(+1) on device; owned iff own_diag_r
   bool own_diag_r = false;
   double *Pdiag = nullptr;  // n (zeros when !hasP)
@@ -41,7 +45,7 @@ struct LinSys {
 
   // A (m x n) and P (n x n upper, may be null) are host CSC matrices.
   int init(Ctx *ctx, const ScsMatrix *Ah, const ScsMatrix *Ph);
-  // build chunk lists and CG work vectors; call after the matrices have their final values
+  // build the tiled SpMV format; call after the matrices have their final (equilibrated) values
   int finalize_structure();
   void destroy();
   int update_precond();  // M = 1 / diag(R_x + P + A' R_y^-1 A)   (private.c:50-84)
@@ -60,6 +64,10 @@ struct LinSys {
   // algorithmic bytes
   double bytes_A() const { return 12.0 * A.nnz + 4.0 * (m + 1) + 8.0 * n + 8.0 * m; }
   double bytes_At() const { return 12.0 * At.nnz + 4.0 * (n + 1) + 8.0 * m + 8.0 * n; }
+  // kernels of one CG iteration (enqueue_cg_iter): two products + two vector updates; a tiled product is
+  // two launches (streaming kernel, epilogue pass)
+  static int tiled_launches(const TiledOp &t) { return t.ok ? (t.has_tiled ? 2 : 1) : 1; }
+  int cg_iter_launches() const { return 2 + tiled_launches(tA) + tiled_launches(tG); }
   double bytes_P() const { return hasP ? 12.0 * P.nnz + 4.0 * (n + 1) + 16.0 * n : 0.0; }
   // launchers shared with the ADMM driver
   int launch_A_scaled(const double *x, double *out, const int *skip, int tag = -1, bool counted = true);  // out = R_y^-1 A x

@@ -944,7 +944,9 @@ static double model_bytes(const SCS_WORK *w, long long iters, long long cg_its, 
 
 // total kernels of this library launched so far: host-counted launches + the CG-loop kernels
 // (4 per CG iteration that really executed; decided on the device)
-static long long total_launches(const SCS_WORK *w, long long cg_its) { return w->c.launches + 4 * cg_its; }
+static long long total_launches(const SCS_WORK *w, long long cg_its) {
+  return w->c.launches + w->ls.cg_iter_launches() * cg_its;
+}
 
 static int set_kt(SCS_WORK *w, int on) {
   Ctx &c = w->c;
@@ -1398,6 +1400,7 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
       }
       if (w->cone.normalize_box(Dh.empty() ? nullptr : Dh.data())) break;
     }
+    if (w->ls.finalize_structure()) { B200_PRINTF("ERROR: tiled SpMV format failure\n"); break; }
     if (scs_update(w, d_full->b, d->c)) break;
     if (w->ls.update_precond()) break;
     if (w->stgs.acceleration_lookback) {
@@ -1682,6 +1685,10 @@ extern "C" scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out) {
   out->d2h_bytes = w->c.d2h;
   out->collectives = w->c.collectives;
   out->collective_bytes = w->c.collective_bytes;
+  out->tiled_a = w->ls.tA.ok ? 1 : 0;
+  out->tiled_g = w->ls.tG.ok ? 1 : 0;
+  out->tiled_slots = (w->ls.tA.ok ? w->ls.tA.slots : 0) + (w->ls.tG.ok ? w->ls.tG.slots : 0);
+  out->tiled_nnz = (w->ls.tA.ok ? w->ls.tA.nnz : 0) + (w->ls.tG.ok ? w->ls.tG.nnz : 0);
   return 0;
 }
 
@@ -1731,4 +1738,24 @@ extern "C" double scs_b200_bench_spmv(ScsWork *w, scs_int which, scs_int reps, d
   cudaEventDestroy(e1);
   if (alg_bytes) *alg_bytes = which == 0 ? ls.bytes_A() : (ls.bytes_At() + ls.bytes_P());
   return (double)ms / reps;
+}
+
+// per-CTA profile of the last launch of a tiled operator (which = 0: A, 1: [A' | P]); out receives
+// 4 doubles per CTA: duration us, us spent streaming non-zeros, modelled cost of its item list, items
+extern "C" scs_int scs_b200_tiled_profile(ScsWork *w, scs_int which, double *out, scs_int cap) {
+  if (!w || !out) return -1;
+  const TiledOp &op = which == 0 ? w->ls.tA : w->ls.tG;
+  if (!op.ok) return 0;
+  const int ncta = op.d.ncta;
+  std::vector<unsigned long long> h((size_t)3 * ncta);
+  if (cudaSetDevice(w->c.device) != cudaSuccess || cudaStreamSynchronize(w->c.stream) != cudaSuccess ||
+      cudaMemcpy(h.data(), op.d.prof, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  for (int b = 0; b < ncta && b < cap; ++b) {
+    out[4 * b + 0] = (double)(h[3 * b + 1] - h[3 * b + 0]) * 1e-3;
+    out[4 * b + 1] = (double)h[3 * b + 2] * 1e-3;
+    out[4 * b + 2] = op.cta_cost[b];
+    out[4 * b + 3] = (double)op.cta_items[b];
+  }
+  return ncta;
 }

@@ -1,0 +1,137 @@
+"""GPU tier: the tiled shared-memory SpMV engine (csrc/tiled.cuh, tiled.cu) behind the same C ABI.
+
+The engine is selected automatically for large matrices; SCS_B200_TILED=1 forces it on small ones so
+that the format builder (segments, padding groups, distinct rows per group), the column-piece split
+with its ticketed combine, and the per-row-bin reduction deposits are exercised on inputs small
+enough to check on the host:
+  * KKT residual of scs_solve_lin_sys recomputed with scipy (tolerance 1e-8 relative, FP64),
+  * agreement with the row engine (SCS_B200_TILED=0) on the same inputs (1e-9 relative),
+  * run-to-run bit-identity (fixed summation order, no atomics on data),
+  * full solves: same status, objectives within 1e-6 relative at eps 1e-9 (north_star tolerance).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from tests import helpers, problems
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def B(gpu):
+    from scs_python_b200 import _scs_b200 as mod
+    return mod
+
+
+@pytest.fixture(scope="module")
+def scsb(gpu):
+    import scs_python_b200
+    return scs_python_b200
+
+
+def _mat(B, M):
+    M = sp.csc_matrix(M); M.sort_indices()
+    x = np.ascontiguousarray(M.data, dtype=np.float64); i = M.indices.astype(np.int32); p = M.indptr.astype(np.int32)
+    return B.make_matrix(x, i, p, M.shape[0], M.shape[1]), (x, i, p)
+
+
+def _kkt_case(seed, m, n, dens, with_P, dense_row=False, empty=False):
+    rng = np.random.RandomState(seed)
+    A = sp.random(m, n, density=dens, format="lil", random_state=rng, data_rvs=rng.randn)
+    if dense_row:          # one row touching every column: longest-run rule of the group builder
+        A[m // 3, :] = rng.randn(n)
+        A[:, n // 2] = rng.randn(m).reshape(-1, 1)   # and one dense column (dense row of A')
+    if empty:              # empty rows and columns: the epilogue must still visit them
+        A[5:40, :] = 0.0
+        A[:, 7:19] = 0.0
+    A = sp.csc_matrix(A); A.eliminate_zeros(); A.sort_indices()
+    Pf = None
+    if with_P:
+        Q = sp.random(n, n, density=min(1.0, 3.0 / n), format="csc", random_state=rng, data_rvs=rng.randn)
+        Pf = sp.csc_matrix(Q @ Q.T + 0.1 * sp.eye(n))
+    diag_r = np.concatenate([np.full(n, 1e-3), 0.5 + rng.rand(m), [10.0]])
+    return A, Pf, diag_r, rng
+
+
+def _solve(B, A, Pf, diag_r, b, s, tol):
+    MA, k1 = _mat(B, A)
+    MP, k2 = _mat(B, sp.triu(Pf, format="csc")) if Pf is not None else (None, None)
+    w = B.lib.scs_init_lin_sys_work(C.byref(MA), C.byref(MP) if MP is not None else None, B._dptr(diag_r))
+    assert w
+    try:
+        out = b.copy()
+        assert B.lib.scs_solve_lin_sys(w, B._dptr(out), B._dptr(s) if s is not None else None, tol) == 0
+        out2 = b.copy()
+        assert B.lib.scs_solve_lin_sys(w, B._dptr(out2), B._dptr(s) if s is not None else None, tol) == 0
+        its = B.lib.scs_b200_lin_sys_cg_its(w)
+    finally:
+        B.lib.scs_free_lin_sys_work(w)
+    return out, out2, its
+
+
+@pytest.mark.parametrize("case", [
+    dict(seed=1, m=3000, n=800, dens=0.01, with_P=True),                       # one row bin, one piece
+    dict(seed=2, m=40000, n=9000, dens=0.002, with_P=True),                    # 3 row bins x 3 column bins, pieces > 1
+    dict(seed=3, m=9000, n=40000, dens=0.002, with_P=False),                   # wide: 10 column bins of A, no P
+    dict(seed=4, m=20000, n=5000, dens=0.001, with_P=True, dense_row=True),    # dense row + dense column
+    dict(seed=5, m=17000, n=4097, dens=0.003, with_P=True, empty=True),        # odd sizes, empty rows / columns
+    dict(seed=6, m=33, n=7, dens=0.5, with_P=False),                           # tiny
+])
+def test_tiled_lin_sys_kkt_residual_and_row_engine_agreement(B, monkeypatch, case):
+    A, Pf, diag_r, rng = _kkt_case(**case)
+    m, n = A.shape
+    b, s = rng.randn(n + m), rng.randn(n)
+    monkeypatch.setenv("SCS_B200_TILED", "1")
+    t1, t2, its_t = _solve(B, A, Pf, diag_r, b, s, 1e-13)
+    monkeypatch.setenv("SCS_B200_TILED", "0")
+    r1, _, its_r = _solve(B, A, Pf, diag_r, b, s, 1e-13)
+    monkeypatch.delenv("SCS_B200_TILED")
+    assert np.array_equal(t1, t2), "tiled engine is not run-to-run deterministic"
+    P = Pf if Pf is not None else sp.csc_matrix((n, n))
+    Kkt = sp.bmat([[sp.diags(diag_r[:n]) + P, A.T], [A, -sp.diags(diag_r[n:n + m])]], format="csr")
+    scale = max(1.0, np.max(np.abs(b)), np.max(np.abs(t1)))
+    assert np.max(np.abs(Kkt @ t1 - b)) <= 1e-8 * scale
+    assert np.max(np.abs(t1 - r1)) <= 1e-9 * scale
+    assert its_t > 0 and its_r > 0
+
+
+@pytest.mark.parametrize("which", ["mixed_cones", "lasso", "socp"])
+def test_tiled_full_solve_matches_row_engine(scsb, monkeypatch, which):
+    if which == "mixed_cones":
+        K = dict(z=4, l=12, q=[3, 5], s=[4], ep=2, ed=1, p=[0.3, -0.6])
+        data, _ = problems.gen_feasible(K, n=25, density=0.3, seed=7, with_P=True)
+    elif which == "lasso":
+        from scs_python_b200 import problems as P
+        data, K, _ = P.lasso(3000, 6000, 30, seed=2)
+    else:
+        from scs_python_b200 import problems as P
+        data, K, _ = P.socp_portfolio(seed=1, n=3000, ncones=600)
+    kw = dict(eps_abs=1e-9, eps_rel=1e-9, max_iters=50000, verbose=False)
+    monkeypatch.setenv("SCS_B200_TILED", "1")
+    a = scsb.SCS(data, K, **kw).solve()
+    a2 = scsb.SCS(data, K, **kw).solve()
+    monkeypatch.setenv("SCS_B200_TILED", "0")
+    b = scsb.SCS(data, K, **kw).solve()
+    monkeypatch.delenv("SCS_B200_TILED")
+    assert a["info"]["status_val"] == b["info"]["status_val"] == 1, (a["info"]["status"], b["info"]["status"])
+    assert np.array_equal(a["x"], a2["x"]) and a["info"]["iter"] == a2["info"]["iter"]
+    for key in ("pobj", "dobj"):
+        assert abs(a["info"][key] - b["info"][key]) <= 1e-6 * max(1.0, abs(b["info"][key])), key
+    helpers.verify_solution(data, K, a, 1e-9, 1e-9, cone_tol=1e-6)
+
+
+def test_tiled_auto_selection_on_large_lasso(scsb):
+    """5.3 M non-zeros: above the size threshold, so the default path is the tiled engine; the result
+    must meet the reference's convergence criteria recomputed on the host, and the engine in use is
+    reported by the workspace statistics."""
+    from scs_python_b200 import problems as P
+    data, cone, _ = P.lasso(50_000, 100_000, 100, seed=4)
+    solver = scsb.SCS(data, cone, verbose=False, max_iters=5000)
+    sol = solver.solve(warm_start=False)
+    assert sol["info"]["status_val"] == 1, sol["info"]["status"]
+    helpers.verify_solution(data, cone, sol, 1e-4, 1e-4, cone_tol=1e-6)
+    st = solver._solver.stats()
+    assert st["tiled_a"] == 1 and st["tiled_g"] == 1, st
