@@ -6,9 +6,10 @@
 //   2. groups per segment = max(ceil(count / 32), longest row run); a column bin that is used by
 //      any warp of a row bin gets at least one (padding) group in every warp, so that all warps
 //      of the CTA step through the same sequence of x-slices;
-//   3. stable radix sort of (segment id -> entry) with CUB: inside a segment the entries keep the
-//      CSR order (row-major); entry number k of a segment goes to group k mod G, lane k div G --
-//      equal rows are consecutive and at most G long, so the rows inside a group are distinct;
+//   3. stable radix sort of ((segment id, row mod 16) -> entry) with CUB: inside a segment the entries
+//      are ordered by the bank pair of their accumulator, then row-major; entry number k of a segment
+//      goes to group k mod G, lane k div G -- equal rows are consecutive and at most G long, so the rows
+//      inside a group are distinct, and every bank pair is spread evenly over the groups;
 //   4. host: split tall row bins into column pieces, assign the work items to the CTAs (longest
 //      first onto the least loaded CTA), upload the schedule.
 #include <algorithm>
@@ -45,7 +46,10 @@ k_tl_count(CsrDev M, int cboff, long long koff, int ncb, unsigned *__restrict__ 
     const long long segb = ((long long)rb * kTW + w) * ncb + cboff;
     for (int k = start + lane; k < end; k += 32) {
       const int cb = M.idx[k] / kTC;
-      key[koff + k] = (unsigned)(segb + cb);
+      // sort key: segment, then the accumulator's bank pair (row mod 16): dealing a segment's entries
+      // round-robin over its groups then spreads every bank pair evenly over the groups, which cuts the
+      // shared-memory bank conflicts of the y read-modify-write (rows of one bank class stay row-major)
+      key[koff + k] = (unsigned)((segb + cb) * 16 + (row & 15));
       rowof[koff + k] = row;
       const bool runstart = (k == start) || (M.idx[k - 1] / kTC != cb);
       if (runstart) {  // length of this row's run inside the column bin: first k2 with idx >= (cb+1) C
@@ -98,7 +102,7 @@ k_tl_scatter(const unsigned *__restrict__ skey, const unsigned *__restrict__ sva
              const int *__restrict__ sstart, const int *__restrict__ gbase, const int *__restrict__ rowof, CsrDev M1,
              CsrDev M2, unsigned *__restrict__ pk, double *__restrict__ val) {
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
-    const unsigned seg = skey[p];
+    const unsigned seg = skey[p] >> 4;
     const unsigned src = sval[p];
     const int k = (int)(p - sstart[seg]);
     const int g0 = gbase[seg], G = gbase[seg + 1] - g0;
@@ -191,7 +195,7 @@ int TiledOp::build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force) {
     size_t tb1 = 0, tb2 = 0, tb3 = 0;
     if (cub::DeviceScan::ExclusiveSum(nullptr, tb1, ng, d.gbase, (int)(nseg + 1), st) != cudaSuccess) break;
     int bits = 1;
-    while ((1ll << bits) < nseg && bits < 32) ++bits;
+    while ((1ll << bits) < nseg * 16 && bits < 32) ++bits;  // key = segment * 16 + bank class
     if (cub::DeviceRadixSort::SortPairs(nullptr, tb2, key, key2, sv, sv2, (int)total, 0, bits, st) != cudaSuccess) break;
     tb3 = tb1 > tb2 ? tb1 : tb2;
     if (cudaMalloc(&tmp, tb3 ? tb3 : 16) != cudaSuccess) break;

@@ -9,6 +9,7 @@ for s in "$@"; do
     sanitize) SCS_B200_TILED=1 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_tiled.py -x -q -k "kkt and (case0 or case4)" > gpurun_out/${tag}_sanitize.txt 2>&1; echo "rc=$?" >> gpurun_out/${tag}_sanitize.txt ;;
     pytest) timeout 900 python -m pytest tests -m gpu -x -q --durations=10 > gpurun_out/${tag}_pytest_gpu.txt 2>&1; echo "rc=$? t=$(( $(date +%s)-t0 ))" >> gpurun_out/${tag}_pytest_gpu.txt ;;
     profile) SCS_B200_TILED_VERBOSE=1 timeout 300 python tools/tiled_profile.py > gpurun_out/${tag}_tiled_profile.txt 2>&1; cat gpurun_out/${tag}_tiled_profile.txt ;;
+    ncug) timeout 400 ncu --set full --clock-control none --import-source on -k regex:tiled -s 28 -c 4 -f -o gpurun_out/${tag}_tiled_g python tools/tiled_profile.py > gpurun_out/${tag}_ncug.log 2>&1; tail -2 gpurun_out/${tag}_ncug.log ;;
     benchq) timeout 300 python bench.py --scale 0.25 --steps 4 --warmup 3 --no-cpu-baseline --no-time-to-eps > gpurun_out/${tag}_bench_quarter.json 2> gpurun_out/${tag}_bench_quarter.err; echo "rc=$? t=$(( $(date +%s)-t0 ))" >> gpurun_out/${tag}_bench_quarter.err ;;
     benchq0) SCS_B200_TILED=0 timeout 300 python bench.py --scale 0.25 --steps 4 --warmup 3 --no-cpu-baseline --no-time-to-eps > gpurun_out/${tag}_bench_quarter_rowengine.json 2> gpurun_out/${tag}_bench_quarter_rowengine.err ;;
     bench) timeout 500 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "rc=$? t=$(( $(date +%s)-t0 ))" >> gpurun_out/${tag}_bench.err ;;
