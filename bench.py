@@ -343,23 +343,28 @@ def run_b200(args):
         nnz_g = desc["nnz_A"] + desc["nnz_P"]
         eng = solver._solver.stats()
         tiled = bool(eng.get("tiled_g"))
-        k_g = ("tiled_kernel<EpiG> (2-D tiled, x-slices by TMA into shared memory, y in shared memory)" if tiled
+        k_g = ("tiled_kernel<0> + tiled_epilogue_kernel<EpiG> (2-D tiled: x-slices by TMA into shared memory, "
+               "accumulators in shared memory; the two launches are timed as one product)" if tiled
                else "row_kernel<ElemMul,ElemMul,EpiG,DUAL>")
-        k_a = ("tiled_kernel<EpiScaleRy>" if eng.get("tiled_a") else "row_kernel<ElemMul,ElemMul,EpiScaleRy>")
+        k_a = ("tiled_kernel<0> + tiled_epilogue_kernel<EpiScaleRy>" if eng.get("tiled_a")
+               else "row_kernel<ElemMul,ElemMul,EpiScaleRy>")
         roofline = dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=ncu_traffic(),
                         kernel=k_g + " (Gp = A' z + P p + R_x p, p'Gp fused)",
                         engine=dict(tiled_a=int(eng.get("tiled_a", 0)), tiled_g=int(eng.get("tiled_g", 0)),
                                     stored_slots_per_nnz=(eng["tiled_slots"] / eng["tiled_nnz"] if eng.get("tiled_nnz") else None)),
                         avg_launch_ms=g_ms, launches_timed=int(mk["spmv_g_launches"]),
-                        timing="device %globaltimer, first CTA start -> last CTA end, every launch inside the timed "
-                               "region (graph WHILE-body launches cannot carry CUDA events)",
+                        timing="device %globaltimer, first CTA start -> last CTA end of the product's last kernel, "
+                               "every product inside the timed region (graph WHILE-body launches cannot carry CUDA "
+                               "events)",
                         isolated_event_ms=iso_g_ms,
                         isolated_event_achieved=(mk["bytes_g"] / (iso_g_ms * 1e-3) / 1e9 if iso_g_ms > 0 else 0.0),
                         algorithmic_bytes_per_launch=mk["bytes_g"], peak_source=peak_src,
                         gather_ceiling_gelem_s=GATHER_CEILING_GELEMS,
                         gather_ceiling_frac=(nnz_g / (g_ms * 1e-3) / 1e9 / GATHER_CEILING_GELEMS if g_ms > 0 else 0.0),
-                        gather_note="one random FP64 operand per stored non-zero: 32 B L2 sector per 8 B; measured "
-                                    "ceiling 272 G gathers/s on B200 (profiles/r1b_gather_probe_*.txt, DESIGN.md 3.1)",
+                        gather_note="row engine only: one random FP64 operand per stored non-zero costs a 32 B L2 sector; "
+                                    "measured ceiling 272 G gathers/s on B200 (profiles/r1b_gather_probe_*.txt, DESIGN.md "
+                                    "3.1).  The tiled engine gathers from shared memory and is not bound by it (frac > 1 "
+                                    "means the ceiling was beaten)",
                         second_kernel=dict(kernel=k_a + " (z = R_y^-1 A p)",
                                            avg_launch_ms=a_ms, launches_timed=int(mk["spmv_a_launches"]),
                                            isolated_event_ms=iso_a_ms,

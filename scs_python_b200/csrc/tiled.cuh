@@ -183,7 +183,7 @@ tiled_kernel(TiledDev T, const double *__restrict__ x1, const double *x2, DevSca
       }
     }
   };
-  constexpr int U = 4;
+  constexpr int U = 8;
   for (int ii = i0; ii < i1; ++ii) {
     const TItem im = T.items[ii];
     const unsigned long long t_item = threadIdx.x == 0 ? gtimer() : 0ull;
