@@ -84,8 +84,8 @@ typedef struct {
   scs_int acceleration_type_1;
   scs_float acceleration_regularization;
   scs_float acceleration_relaxation;
-  const char *write_data_filename; /* accepted, ignored by this backend (rw.c out of scope) */
-  const char *log_csv_filename;    /* accepted, ignored by this backend (rw.c out of scope) */
+  const char *write_data_filename; /* scs_init dumps the problem there (S/src/rw.c:240-260 format) */
+  const char *log_csv_filename;    /* scs_solve appends one row per iteration (S/src/rw.c:317-476) */
 } ScsSettings;
 
 /* S/include/scs.h:104-119 */
@@ -168,6 +168,16 @@ scs_int scs(const ScsData *d, const ScsCone *k, const ScsSettings *stgs,
             ScsSolution *sol, ScsInfo *info);                                   /* scs.h:323 */
 void scs_set_default_settings(ScsSettings *stgs);                               /* scs.h:331 */
 const char *scs_version(void);                                                  /* scs.h:338 */
+
+/* Problem data files, S/include/rw.h:15-21 (SCS(write_data) / SCS(read_data), S/src/rw.c:240-315): the
+ * reference's native binary layout, readable and writable by either library (integer width of the
+ * file is converted on read).  write: target is stgs->write_data_filename; read: allocates *d, *k,
+ * *stgs, released with scs_b200_free_data (SCS(free_data), S/src/util.c).  Host only, no device. */
+scs_int scs_b200_write_data(const ScsData *d, const ScsCone *k, const ScsSettings *stgs);
+scs_int scs_b200_read_data(const char *filename, ScsData **d, ScsCone **k, ScsSettings **stgs);
+void scs_b200_free_data(ScsData *d, ScsCone *k, ScsSettings *stgs);
+/* header line of the per-iteration CSV trace (S/src/rw.c:333-402, without the spectral-cone columns) */
+const char *scs_b200_csv_header(void);
 
 /* ---------------------------------------------------------------------------------- */
 /* (2) linear-system plugin ABI -- S/include/linsys.h:25-71.  Host pointers in and     */

@@ -168,6 +168,21 @@ def solve_batch(problems, **settings):
     return _scs.solve_batch([_prepare(d, k) for d, k in problems], **settings)
 
 
+def read_data(filename):
+    """Read a problem file in the reference's binary layout (written by `write_data_filename=...` of either
+    library, or S/test/problems/*): returns (data, cone, settings) ready for `SCS(data, cone, **settings)`.
+    Reference: SCS(read_data), S/src/rw.c:262-315, used by S/test/run_from_file.c."""
+    return _load_b200().read_data(filename)
+
+
+def write_data(filename, data, cone, **settings):
+    """Write (data, cone, settings) in that layout without building a workspace (SCS(write_data),
+    S/src/rw.c:240-260).  `SCS(data, cone, write_data_filename=...)` does the same at construction."""
+    settings = dict(settings)
+    settings.pop("linear_solver", None)
+    return _load_b200().write_data(filename, *_prepare(data, cone), **settings)
+
+
 def solve(data, cone, **settings):
     """Legacy one-shot API (scs/py/__init__.py:217-230)."""
     solver = SCS(data, cone, **settings)

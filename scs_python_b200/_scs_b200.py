@@ -163,6 +163,15 @@ lib.scs_b200_get_marks.restype = c_int
 lib.scs_b200_get_marks.argtypes = [C.c_void_p, C.POINTER(ScsB200Marks)]
 lib.scs_b200_bench_spmv.restype = c_double
 lib.scs_b200_bench_spmv.argtypes = [C.c_void_p, c_int, c_int, p_double]
+lib.scs_b200_write_data.restype = c_int
+lib.scs_b200_write_data.argtypes = [C.POINTER(ScsData), C.POINTER(ScsCone), C.POINTER(ScsSettings)]
+lib.scs_b200_read_data.restype = c_int
+lib.scs_b200_read_data.argtypes = [C.c_char_p, C.POINTER(C.POINTER(ScsData)), C.POINTER(C.POINTER(ScsCone)),
+                                   C.POINTER(C.POINTER(ScsSettings))]
+lib.scs_b200_free_data.restype = None
+lib.scs_b200_free_data.argtypes = [C.POINTER(ScsData), C.POINTER(ScsCone), C.POINTER(ScsSettings)]
+lib.scs_b200_csv_header.restype = C.c_char_p
+lib.scs_b200_csv_header.argtypes = []
 lib.scs_b200_tiled_profile.restype = c_int
 lib.scs_b200_tiled_profile.argtypes = [C.c_void_p, c_int, p_double, c_int]
 lib.scs_b200_solve_batch.restype = c_int
@@ -395,6 +404,66 @@ _INFO_KEYS = ("status_val", "iter", "scale_updates", "scale", "pobj", "dobj", "r
               "lin_sys_time", "cone_time", "accel_time", "rejected_accel_steps", "accepted_accel_steps")
 _AA_KEYS = ("iter", "n_accept", "n_reject_lapack", "n_reject_rank0", "n_reject_nonfinite",
             "n_reject_weight_cap", "n_safeguard_reject", "last_rank", "last_aa_norm", "last_regularization")
+
+
+def read_data(filename):
+    """SCS(read_data), S/src/rw.c:262-315 (what S/test/run_from_file.c does before solving): a problem
+    file in the reference's binary layout -> (data, cone, settings) with data = dict(A, P, b, c) holding
+    scipy CSC matrices.  Raises ValueError when the file cannot be read."""
+    import scipy.sparse as sp
+    d, k, st = C.POINTER(ScsData)(), C.POINTER(ScsCone)(), C.POINTER(ScsSettings)()
+    if lib.scs_b200_read_data(os.fsencode(filename), C.byref(d), C.byref(k), C.byref(st)) != 0:
+        raise ValueError("could not read SCS data file %r" % (filename,))
+    try:
+        D, K, S = d.contents, k.contents, st.contents
+
+        def mat(M):
+            nnz = M.p[M.n]
+            return sp.csc_matrix((np.array(M.x[:nnz], dtype=np.float64), np.array(M.i[:nnz], dtype=np.int32),
+                                  np.array(M.p[:M.n + 1], dtype=np.int32)), shape=(M.m, M.n))
+        data = dict(A=mat(D.A.contents), b=np.array(D.b[:D.m], dtype=np.float64), c=np.array(D.c[:D.n], dtype=np.float64))
+        data["P"] = mat(D.P.contents) if D.P else None
+        cone = dict(z=K.z, l=K.l, ep=K.ep, ed=K.ed)
+        if K.bsize > 1:
+            cone["bl"] = np.array(K.bl[:K.bsize - 1], dtype=np.float64)
+            cone["bu"] = np.array(K.bu[:K.bsize - 1], dtype=np.float64)
+        if K.qsize > 0:
+            cone["q"] = [int(v) for v in K.q[:K.qsize]]
+        if K.ssize > 0:
+            cone["s"] = [int(v) for v in K.s[:K.ssize]]
+        if K.psize > 0:
+            cone["p"] = [float(v) for v in K.p[:K.psize]]
+        settings = dict(normalize=bool(S.normalize), scale=S.scale, rho_x=S.rho_x, max_iters=S.max_iters,
+                        eps_abs=S.eps_abs, eps_rel=S.eps_rel, eps_infeas=S.eps_infeas, alpha=S.alpha,
+                        verbose=bool(S.verbose), acceleration_lookback=S.acceleration_lookback,
+                        acceleration_interval=S.acceleration_interval, acceleration_type_1=S.acceleration_type_1,
+                        acceleration_regularization=S.acceleration_regularization,
+                        acceleration_relaxation=S.acceleration_relaxation, adaptive_scale=bool(S.adaptive_scale))
+    finally:
+        lib.scs_b200_free_data(d, k, st)
+    return data, cone, settings
+
+
+def write_data(filename, shape, Ax, Ai, Ap, Px, Pi, Pp, b, c, cone, **settings):
+    """SCS(write_data), S/src/rw.c:240-260, without creating a workspace (no device needed)."""
+    m, n = shape
+    A = make_matrix(Ax, Ai, Ap, m, n)
+    data = ScsData()
+    data.m, data.n = m, n
+    data.A = C.pointer(A)
+    P = None
+    if Px is not None:
+        P = make_matrix(Px, Pi, Pp, n, n)
+        data.P = C.pointer(P)
+    data.b, data.c = _dptr(b), _dptr(c)
+    k, keep = make_cone(cone)
+    st, keep2 = make_settings(dict(settings, write_data_filename=os.fspath(filename)))
+    if lib.scs_b200_write_data(C.byref(data), C.byref(k), C.byref(st)) != 0:
+        raise ValueError("could not write SCS data file %r" % (filename,))
+
+
+def csv_header():
+    return lib.scs_b200_csv_header().decode()
 
 
 def _info_dict(info):

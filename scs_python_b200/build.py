@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libscsb200.so")
-SOURCES = ["sparse.cu", "tiled.cu", "linsys.cu", "cones.cu", "aa.cu", "dist.cu", "scs_solver.cu", "batch.cu"]
+SOURCES = ["sparse.cu", "tiled.cu", "linsys.cu", "cones.cu", "aa.cu", "dist.cu", "scs_solver.cu", "batch.cu", "rw.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=default", "--expt-relaxed-constexpr"]
 

@@ -484,6 +484,47 @@ k_scale3(double *__restrict__ x, int n, double fx, double *__restrict__ y, doubl
   }
 }
 
+// ---- CSV trace (SCS(log_data_to_csv), rw.c:317-476): the vector norms of one row that the residual
+// epilogues do not already deliver.  ax = A x (m), atp = A'y + P x (n), both in normalised scaling.
+// out (S->part): 12 sums of squares then 8 maxima, see csv_log().
+__global__ void __launch_bounds__(kThreads)
+k_csv_norms(const double *__restrict__ u, const double *__restrict__ u_t, const double *__restrict__ v,
+            const double *__restrict__ v_prev, const double *__restrict__ rsk, const double *__restrict__ ax,
+            const double *__restrict__ atp, const double *__restrict__ b, const double *__restrict__ c,
+            const double *__restrict__ D, const double *__restrict__ E, int n, int m, double primal_scale,
+            double dual_scale, RedWs red, DevScalars *S) {
+  double o[20];
+#pragma unroll
+  for (int k = 0; k < 20; ++k) o[k] = 0.0;
+  const int l = n + m + 1;
+  const double tau = fabs(u[n + m]);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x) {
+    const double du = u[j] - u_t[j], dv = v[j] - v_prev[j];
+    o[10] = fma(du, du, o[10]); o[11] = fma(dv, dv, o[11]);
+    o[18] = fmax(o[18], fabs(du)); o[19] = fmax(o[19], fabs(dv));
+    if (j < n) {
+      const double x = u[j], xo = x * (E[j] / dual_scale);
+      const double r = atp[j] + tau * c[j], ro = r / (E[j] * primal_scale);
+      o[0] = fma(x, x, o[0]); o[3] = fma(xo, xo, o[3]);
+      o[12] = fmax(o[12], fabs(x)); o[15] = fmax(o[15], fabs(xo));
+      o[7] = fma(r, r, o[7]); o[9] = fma(ro, ro, o[9]);
+    } else if (j < n + m) {
+      const int i = j - n;
+      const double y = u[j], s = rsk[j];
+      const double yo = y * (D[i] / primal_scale), so = s / (D[i] * dual_scale);
+      const double r = ax[i] + s - tau * b[i], ro = r / (D[i] * dual_scale);
+      o[1] = fma(y, y, o[1]); o[2] = fma(s, s, o[2]); o[4] = fma(yo, yo, o[4]); o[5] = fma(so, so, o[5]);
+      o[13] = fmax(o[13], fabs(y)); o[14] = fmax(o[14], fabs(s));
+      o[16] = fmax(o[16], fabs(yo)); o[17] = fmax(o[17], fabs(so));
+      o[6] = fma(r, r, o[6]); o[8] = fma(ro, ro, o[8]);
+    }
+  }
+  grid_reduce<12, 8>(o, red, [S](double *q) {
+#pragma unroll
+    for (int k = 0; k < 20; ++k) S->part[k] = q[k];
+  });
+}
+
 // ---------------------------------------------------------- host-side structures -------
 struct HostResid {  // ScsResiduals scalars (scs_work.h:29-50); vectors are reduced on the device
   int last_iter = -1;
@@ -533,6 +574,7 @@ struct SCS_WORK {
   double *u = nullptr, *u_t = nullptr, *v = nullptr, *v_prev = nullptr, *rsk = nullptr, *g = nullptr;
   double *diag_r = nullptr, *b = nullptr, *cvec = nullptr, *D = nullptr, *E = nullptr, *ws = nullptr;
   double *sol_x = nullptr, *sol_y = nullptr, *sol_s = nullptr;
+  double *csv_m = nullptr, *csv_n = nullptr;  // A x and A'y + P x of the CSV trace (allocated on first use)
   // host
   std::vector<double> b_orig, c_orig;
   double nm_b_orig = 0, nm_c_orig = 0, primal_scale = 1, dual_scale = 1;
@@ -881,6 +923,68 @@ static int populate_residuals(SCS_WORK *w, int iter) {
   return 0;
 }
 
+// SCS(log_data_to_csv), rw.c:317-476: one row per call, file opened "w" at iteration 0 and "a" afterwards.
+// Costs two SpMV passes, one reduction and a host sync per row, like the reference's per-iteration
+// populate_residual_struct (scs.c:1396-1401).
+static int csv_log(SCS_WORK *w, int iter, const Clock::time_point &t0) {
+  Ctx &c = w->c;
+  LinSys &ls = w->ls;
+  const int n = w->n, m = w->m;
+  if (populate_residuals(w, iter)) return -1;
+  if (!w->csv_m && (dev_alloc(&w->csv_m, (size_t)m) || dev_alloc(&w->csv_n, (size_t)n))) return -1;
+  {
+    EpiStore es; es.y = w->csv_m;
+    ElemMul e{w->u};
+    row_kernel<ElemMul, ElemMul, EpiStore, false>
+        <<<ls.chA.grid, kThreads, 0, c.stream>>>(ls.A, e, ls.A, e, ls.chA.d, ls.chA.n, es, c.red, c.S, nullptr);
+    EpiStore et; et.y = w->csv_n;
+    ElemMul ea{w->u + n}, eb{w->u};
+    if (ls.hasP)
+      row_kernel<ElemMul, ElemMul, EpiStore, true>
+          <<<ls.chAt.grid, kThreads, 0, c.stream>>>(ls.At, ea, ls.P, eb, ls.chAt.d, ls.chAt.n, et, c.red, c.S, nullptr);
+    else
+      row_kernel<ElemMul, ElemMul, EpiStore, false>
+          <<<ls.chAt.grid, kThreads, 0, c.stream>>>(ls.At, ea, ls.P, eb, ls.chAt.d, ls.chAt.n, et, c.red, c.S, nullptr);
+    k_csv_norms<<<ew_grid(c, w->l), kThreads, 0, c.stream>>>(w->u, w->u_t, w->v, w->v_prev, w->rsk, w->csv_m, w->csv_n,
+                                                             w->b, w->cvec, w->D, w->E, n, m, w->primal_scale,
+                                                             w->dual_scale, c.red, c.S);
+    c.launches += 3; c.spmv_calls += 2;
+  }
+  if (c.fetch_scalars()) return -1;
+  const double *q = c.S_host->part;
+  FILE *f = fopen(w->csv_fn.c_str(), iter == 0 ? "w" : "a");
+  if (!f) {
+    B200_PRINTF("Error: Could not open %s for writing\n", w->csv_fn.c_str());
+    return 0;
+  }
+  if (iter == 0) fprintf(f, "%s\n", scs_b200_csv_header());
+  const HostResid &r = w->r_o, &rn = w->r_n;
+  const bool nrm = w->stgs.normalize != 0;
+  auto F = [f](double v) { fprintf(f, "%.16e,", v); };
+  fprintf(f, "%li,", (long)iter);
+  F(r.res_pri); F(r.res_dual); F(r.gap);
+  // un-normalised then normalised solution norms (identical without equilibration)
+  F(nrm ? q[15] : q[12]); F(nrm ? q[16] : q[13]); F(nrm ? q[17] : q[14]);
+  F(sqrt(nrm ? q[3] : q[0])); F(sqrt(nrm ? q[4] : q[1])); F(sqrt(nrm ? q[5] : q[2]));
+  F(q[12]); F(q[13]); F(q[14]); F(sqrt(q[0])); F(sqrt(q[1])); F(sqrt(q[2]));
+  F(r.nm_ax_s_btau); F(r.nm_px_aty_ctau); F(sqrt(nrm ? q[8] : q[6])); F(sqrt(nrm ? q[9] : q[7]));
+  F(r.res_infeas); F(r.res_unbdd_a); F(r.res_unbdd_p); F(r.pobj); F(r.dobj); F(r.tau); F(r.kap);
+  F(rn.res_pri); F(rn.res_dual); F(rn.gap);
+  F(rn.nm_ax_s_btau); F(rn.nm_px_aty_ctau); F(sqrt(q[6])); F(sqrt(q[7]));
+  F(rn.res_infeas); F(rn.res_unbdd_a); F(rn.res_unbdd_p); F(rn.pobj); F(rn.dobj); F(rn.tau); F(rn.kap);
+  F(r.nm_ax); F(r.nm_ax_s); F(r.nm_px); F(r.nm_aty);
+  F(r.xt_p_x); F(r.xt_p_x_tau); F(r.ctx); F(r.ctx_tau); F(r.bty); F(r.bty_tau);
+  F(w->nm_b_orig); F(w->nm_c_orig); F(w->stgs.scale);
+  F(sqrt(q[10])); F(sqrt(q[11])); F(q[18]); F(q[19]);
+  F(c.S_host->aa_norm);
+  fprintf(f, "%li,", (long)c.S_host->aa_accepted);
+  fprintf(f, "%li,", (long)c.S_host->aa_rejected);
+  F(ms_since(t0) / 1e3);
+  fprintf(f, "\n");
+  fclose(f);
+  return 0;
+}
+
 // has_converged, scs.c:589-627 (isless() == NaN-safe '<')
 static int has_converged(const SCS_WORK *w) {
   const HostResid &r = w->r_o;
@@ -1102,6 +1206,7 @@ static void free_work(SCS_WORK *w) {
   dev_free(w->u); dev_free(w->u_t); dev_free(w->v); dev_free(w->v_prev); dev_free(w->rsk); dev_free(w->g);
   dev_free(w->diag_r); dev_free(w->b); dev_free(w->cvec); dev_free(w->D); dev_free(w->E); dev_free(w->ws);
   dev_free(w->sol_x); dev_free(w->sol_y); dev_free(w->sol_s); dev_free(w->gather);
+  dev_free(w->csv_m); dev_free(w->csv_n);
   w->c.destroy();
   delete w;
 }
@@ -1354,9 +1459,16 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
   if (w->stgs.verbose) print_init_header(d_full, k_full, &w->stgs);
   w->n = d->n; w->m = d->m; w->l = d->n + d->m + 1;
   const int n = w->n, m = w->m, l = w->l;
-  if (stgs->write_data_filename) w->write_fn = stgs->write_data_filename;
-  if (stgs->log_csv_filename) w->csv_fn = stgs->log_csv_filename;
-  w->stgs.write_data_filename = nullptr;  // rw.c is out of scope for this backend
+  if (stgs->write_data_filename) {  // scs.c:1219-1222 (the full problem, before any partitioning)
+    B200_PRINTF("Writing raw problem data to %s\n", stgs->write_data_filename);
+    scs_b200_write_data(d_full, k_full, stgs);
+    w->write_fn = stgs->write_data_filename;
+  }
+  if (stgs->log_csv_filename) {  // scs.c:1223-1226
+    B200_PRINTF("Logging run data to %s\n", stgs->log_csv_filename);
+    w->csv_fn = stgs->log_csv_filename;
+  }
+  w->stgs.write_data_filename = nullptr;  // the workspace keeps its own copies of the names
   w->stgs.log_csv_filename = nullptr;
   bool ok = false;
   do {
@@ -1470,6 +1582,7 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
 
   const int gl = ew_grid(c, l);
   const bool accel = w->has_aa;
+  const bool csv = !w->csv_fn.empty() && !w->dist;  // the row-partitioned mode writes no trace
   const int interval = stgs->acceleration_interval;
   {  // device-side loop state of this solve: iteration index and phase clocks
     static const unsigned long long zeros[5] = {0, 0, 0, 0, 0};
@@ -1538,7 +1651,11 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
       k_stamp<<<1, 1, 0, st>>>(c.S, 2);
       c.launches += 2;
     }
+    // ---- CSV trace, after the scale update so that the extra residual pass does not touch the
+    //      algorithm (scs.c:1396-1401)
+    if (csv && csv_log(w, i, t0)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in the CSV trace", "failure");
   }
+  if (csv && csv_log(w, i, t0)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in the CSV trace", "failure");
   if (w->mk_open) mark_close(w, i);
   w->mark_begin = w->mark_end = -1;
   w->admm_iters += i;
