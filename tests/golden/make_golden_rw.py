@@ -34,8 +34,10 @@ def rw_problem():
 
 def trace_problem():
     from tests import problems
-    K = dict(z=4, l=12, q=[3, 5], ep=2)
-    data, _ = problems.gen_feasible(K, n=20, density=0.3, seed=5, with_P=True)
+    # m = 139 rows for n = 30 columns: a well-conditioned reduced system, so that the first iterations do
+    # not depend on where a loosely converged CG happens to stop (see tests/test_gpu_rw.py)
+    K = dict(z=10, l=60, q=[10, 20, 15], ep=5, ed=3)
+    data, _ = problems.gen_feasible(K, n=30, density=0.5, seed=5, with_P=True)
     return data, K, dict(eps_abs=1e-6, eps_rel=1e-6)
 
 
