@@ -986,6 +986,53 @@ static void status_string(int status_val, int iter, int max_iters, char *out) {
   }
 }
 
+// Pinned host staging, device pools, stream and events of the batch engine are kept per host thread and
+// only ever grow: a pinned allocation costs milliseconds per megabyte, which dominated the wall time of a
+// 1024-problem batch (profiles/r1f_configs_b200.jsonl: 228 ms of "packing" next to 121 ms of kernel).
+// They live until the process exits (thread_local objects with CUDA destructors would run after the driver
+// has shut down).
+struct BatchArena {
+  int dev = -1;
+  void *h[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t hcap[4] = {0, 0, 0, 0};
+  void *d[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t dcap[7] = {0, 0, 0, 0, 0, 0, 0};
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  void release() {
+    for (int k = 0; k < 4; ++k) { if (h[k]) cudaFreeHost(h[k]); h[k] = nullptr; hcap[k] = 0; }
+    for (int k = 0; k < 7; ++k) { if (d[k]) cudaFree(d[k]); d[k] = nullptr; dcap[k] = 0; }
+    if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    e0 = e1 = nullptr; st = nullptr;
+  }
+  cudaError_t host(int k, size_t bytes, void **out) {
+    if (hcap[k] < bytes) {
+      if (h[k]) cudaFreeHost(h[k]);
+      h[k] = nullptr; hcap[k] = 0;
+      const size_t cap = bytes + bytes / 4 + 256;
+      const cudaError_t e = cudaMallocHost(&h[k], cap);
+      if (e != cudaSuccess) return e;
+      hcap[k] = cap;
+    }
+    *out = h[k];
+    return cudaSuccess;
+  }
+  cudaError_t device(int k, size_t bytes, void **out) {
+    if (dcap[k] < bytes) {
+      if (d[k]) cudaFree(d[k]);
+      d[k] = nullptr; dcap[k] = 0;
+      const size_t cap = bytes + bytes / 4 + 256;
+      const cudaError_t e = cudaMalloc(&d[k], cap);
+      if (e != cudaSuccess) return e;
+      dcap[k] = cap;
+    }
+    *out = d[k];
+    return cudaSuccess;
+  }
+};
+static thread_local BatchArena g_arena;
+
 struct BatchStats { long long fused = 0, streamed = 0, launches = 0, h2d = 0, d2h = 0, cg_its = 0, iters = 0, clk[6] = {0, 0, 0, 0, 0, 0}; double kernel_ms = 0, pack_ms = 0; int ctas = 0, smem = 0, direct = 0; };
 static BatchStats g_last_batch;
 
@@ -1051,11 +1098,13 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
       itot = (itot + 7) & ~7ll;
       stot += p.n + 2ll * p.m;
     }
+    BatchArena &ar = g_arena;
+    if (ar.dev != dev) { ar.release(); ar.dev = dev; }
     double *h_d = nullptr; u16 *h_i = nullptr; double *h_sol = nullptr; BOut *h_out = nullptr;
-    if (cudaMallocHost(&h_d, sizeof(double) * (size_t)std::max(1ll, dtot)) != cudaSuccess ||
-        cudaMallocHost(&h_i, sizeof(u16) * (size_t)std::max(1ll, itot)) != cudaSuccess ||
-        cudaMallocHost(&h_sol, sizeof(double) * (size_t)std::max(1ll, stot)) != cudaSuccess ||
-        cudaMallocHost(&h_out, sizeof(BOut) * (size_t)nf) != cudaSuccess) {
+    if (ar.host(0, sizeof(double) * (size_t)std::max(1ll, dtot), (void **)&h_d) != cudaSuccess ||
+        ar.host(1, sizeof(u16) * (size_t)std::max(1ll, itot), (void **)&h_i) != cudaSuccess ||
+        ar.host(2, sizeof(double) * (size_t)std::max(1ll, stot), (void **)&h_sol) != cudaSuccess ||
+        ar.host(3, sizeof(BOut) * (size_t)nf, (void **)&h_out) != cudaSuccess) {
       fprintf(stderr, "libscsb200: batch: pinned allocation failed\n");
       return -1;
     }
@@ -1121,15 +1170,10 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
     double *d_d = nullptr, *d_sol = nullptr, *d_aa = nullptr; u16 *d_i = nullptr; BProb *d_p = nullptr; BOut *d_o = nullptr;
     int *d_cnt = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    auto cleanup = [&]() {
-      if (d_d) cudaFree(d_d); if (d_sol) cudaFree(d_sol); if (d_aa) cudaFree(d_aa); if (d_i) cudaFree(d_i);
-      if (d_p) cudaFree(d_p); if (d_o) cudaFree(d_o); if (d_cnt) cudaFree(d_cnt);
-      if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
-      if (st) cudaStreamDestroy(st);
-      cudaFreeHost(h_d); cudaFreeHost(h_i); cudaFreeHost(h_sol); cudaFreeHost(h_out);
-    };
+    auto cleanup = [&]() {};  // everything below belongs to the thread's arena
 #define BCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fprintf(stderr, "libscsb200: batch: %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); rc = -1; } } while (0)
-    BCK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (!ar.st) BCK(cudaStreamCreateWithFlags(&ar.st, cudaStreamNonBlocking));
+    st = ar.st;
     BCK(cudaFuncSetAttribute(k_batch_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     if (!rc) BCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_batch_solve, kBT, smem));
@@ -1137,13 +1181,13 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
     const int grid = rc ? 0 : std::min(nf, sms * occ);
     const size_t aa_stride = (aaws_count(dims) + 1) & ~(size_t)1;
     if (!rc) {
-      BCK(cudaMalloc(&d_d, sizeof(double) * (size_t)std::max(1ll, dtot)));
-      BCK(cudaMalloc(&d_i, sizeof(u16) * (size_t)std::max(1ll, itot)));
-      BCK(cudaMalloc(&d_sol, sizeof(double) * (size_t)std::max(1ll, stot)));
-      BCK(cudaMalloc(&d_p, sizeof(BProb) * (size_t)nf));
-      BCK(cudaMalloc(&d_o, sizeof(BOut) * (size_t)nf));
-      BCK(cudaMalloc(&d_cnt, sizeof(int)));
-      BCK(cudaMalloc(&d_aa, sizeof(double) * std::max<size_t>(1, aa_stride * (size_t)grid)));
+      BCK(ar.device(0, sizeof(double) * (size_t)std::max(1ll, dtot), (void **)&d_d));
+      BCK(ar.device(1, sizeof(u16) * (size_t)std::max(1ll, itot), (void **)&d_i));
+      BCK(ar.device(2, sizeof(double) * (size_t)std::max(1ll, stot), (void **)&d_sol));
+      BCK(ar.device(3, sizeof(BProb) * (size_t)nf, (void **)&d_p));
+      BCK(ar.device(4, sizeof(BOut) * (size_t)nf, (void **)&d_o));
+      BCK(ar.device(5, sizeof(int), (void **)&d_cnt));
+      BCK(ar.device(6, sizeof(double) * std::max<size_t>(1, aa_stride * (size_t)grid), (void **)&d_aa));
     }
     if (!rc) {
       BCK(cudaMemcpyAsync(d_d, h_d, sizeof(double) * (size_t)dtot, cudaMemcpyHostToDevice, st));
@@ -1163,7 +1207,8 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
         a.stg.pad = 0;
       }
       a.dpool = d_d; a.ipool = d_i; a.sol = d_sol; a.out = d_o; a.aaws = d_aa; a.aaws_stride = aa_stride; a.counter = d_cnt;
-      BCK(cudaEventCreate(&e0)); BCK(cudaEventCreate(&e1));
+      if (!ar.e0) { BCK(cudaEventCreate(&ar.e0)); BCK(cudaEventCreate(&ar.e1)); }
+      e0 = ar.e0; e1 = ar.e1;
       BCK(cudaEventRecord(e0, st));
       k_batch_solve<<<grid, kBT, smem, st>>>(a);
       BCK(cudaGetLastError());

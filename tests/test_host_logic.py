@@ -165,3 +165,54 @@ def test_row_partition_world_size_2_gloo(tmp_path):
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     p0, p1 = out["parts"]
     assert out["world"] == 2 and p0["row0"] == 0 and p0["m"] == p1["row0"] and p0["m"] + p1["m"] == out["m"]
+
+
+def test_solve_batch_wrapper_fills_the_c_structures(monkeypatch):
+    """The batch wrapper fills five contiguous arrays of C structures through integer addresses; read them
+    back through the typed-pointer view the library gets, without a device (the C entry point is replaced
+    by a checker that also writes into the solution block)."""
+    import scipy.sparse as sp
+    import scs_python_b200 as scsb
+    from scs_python_b200 import _scs_b200 as B
+    rng = np.random.RandomState(0)
+    probs = []
+    for i in range(5):
+        m, n = 7 + i, 3 + i
+        A = sp.random(m, n, density=0.6, format="csc", random_state=rng, data_rvs=rng.randn)
+        d = dict(A=A, b=rng.randn(m), c=rng.randn(n))
+        if i % 2 == 0:
+            d["P"] = sp.eye(n, format="csc") * (1.0 + i)
+        cone = dict(z=1, l=m - 4, q=[3]) if i != 3 else dict(l=m - 3, ep=1)   # i == 3: general cone path
+        probs.append((d, cone))
+    prepared = [scsb._prepare(d, k) for d, k in probs]
+    seen = {}
+
+    def fake(cnt, pd, pk, st, ps, infos, z):
+        assert cnt == 5 and st._obj.max_iters == 77      # C.byref(settings)
+        for i in range(cnt):
+            d, k, s = pd[i].contents, pk[i].contents, ps[i].contents
+            A = d.A.contents
+            nnz = A.p[A.n]
+            seen[i] = dict(m=d.m, n=d.n, Am=A.m, An=A.n, Ax=[A.x[j] for j in range(nnz)], Ai=[A.i[j] for j in range(nnz)],
+                           b=[d.b[j] for j in range(d.m)], c=[d.c[j] for j in range(d.n)],
+                           P=[d.P.contents.x[j] for j in range(d.P.contents.p[d.n])] if d.P else None,
+                           z=k.z, l=k.l, q=[k.q[j] for j in range(k.qsize)], ep=k.ep, bsize=k.bsize, ssize=k.ssize)
+            s.x[0], s.y[d.m - 1], s.s[0] = 1.5 + i, 2.5 + i, 3.5 + i
+            infos[i].iter = 10 + i
+        return 0
+    monkeypatch.setattr(B.lib, "scs_b200_solve_batch", fake)
+    res = B.solve_batch(prepared, verbose=False, max_iters=77)
+    for i, ((d, cone), pr) in enumerate(zip(probs, prepared)):
+        shape, Ax, Ai, Ap, Px, Pi, Pp, b, c, _ = pr
+        e = seen[i]
+        assert (e["m"], e["n"], e["Am"], e["An"]) == (shape[0], shape[1], shape[0], shape[1])
+        assert e["Ax"] == list(Ax) and e["Ai"] == list(Ai) and e["b"] == list(b) and e["c"] == list(c)
+        assert e["P"] == (list(Px) if Px is not None else None)
+        assert (e["z"], e["l"], e["q"], e["ep"]) == (cone.get("z", 0), cone.get("l", 0), list(cone.get("q", [])), cone.get("ep", 0))
+        assert e["bsize"] == 0 and e["ssize"] == 0
+        assert res[i]["x"][0] == 1.5 + i and res[i]["y"][-1] == 2.5 + i and res[i]["s"][0] == 3.5 + i
+        assert res[i]["x"].shape == (shape[1],) and res[i]["y"].shape == (shape[0],) and res[i]["info"]["iter"] == 10 + i
+    with pytest.raises(ValueError):
+        B.solve_batch([prepared[0][:8] + (np.zeros(2), prepared[0][9])], verbose=False)   # c of the wrong length
+    with pytest.raises(TypeError):
+        B.solve_batch([prepared[0][:1] + (np.zeros(3, dtype=np.int32),) + prepared[0][2:]], verbose=False)  # Ax not float
