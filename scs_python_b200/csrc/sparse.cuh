@@ -38,13 +38,12 @@ struct ChunkList {
 // Build the chunk list on the host from one or two row-pointer arrays (second may be null;
 // used to fuse P's rows with A' rows).  Greedy: close a chunk when it holds >= target nnz,
 // >= max_rows rows, or the row-length class changes by more than 2x.
-// Rows [row_begin, nrows) are covered; the list is appended to `out` unless row_begin == 0.
-inline void build_chunks_host(int nrows, const int *ptr1, const int *ptr2, std::vector<int4> &out, int row_begin = 0) {
+inline void build_chunks_host(int nrows, const int *ptr1, const int *ptr2, std::vector<int4> &out) {
   const long long target = 4096;
   const int max_rows = 2048;
   const long long long_row = 16384;
-  if (row_begin == 0) out.clear();
-  int r = row_begin;
+  out.clear();
+  int r = 0;
   auto rowlen = [&](int i) -> long long {
     long long L = (long long)ptr1[i + 1] - ptr1[i];
     if (ptr2) L += (long long)ptr2[i + 1] - ptr2[i];

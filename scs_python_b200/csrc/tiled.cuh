@@ -49,7 +49,6 @@ constexpr int kTStages = 3;            // x-slice stages
 constexpr int kTRW = kTR / kTW;        // rows one warp owns inside a row bin
 constexpr unsigned kTFlag = 1u << 12;  // set in the first group of a (warp, column bin) segment
 constexpr int kTRowShift = 13;         // packed entry: local row << 13 | flag << 12 | local column
-constexpr int kTMaxPieces = 16;
 constexpr size_t kTSmem = (size_t)(kTR + 32) * 8 + (size_t)kTStages * kTC * 8 + 64;
 
 // one work item: a row bin restricted to a contiguous range of its active column bins
