@@ -101,3 +101,24 @@ def test_write_data_filename_at_init(gpu, tmp_path):
     s2 = scsb.SCS(data, K, verbose=False, **stg).solve()
     assert s1["info"]["status_val"] == s2["info"]["status_val"] and s1["info"]["iter"] == s2["info"]["iter"]
     assert np.array_equal(s1["x"], s2["x"])
+
+
+def test_plain_c_client_runs_from_file(gpu, tmp_path):
+    """tools/c/run_from_file.c (gcc, no Python): read the reference-written file, solve on the device, write a
+    trace -- the C ABI used the way S/test/run_from_file.c uses the reference core."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(HERE), "tools", "c", "_bin", "run_from_file")
+    if not os.path.exists(exe):
+        pytest.skip("tools/c/_bin/run_from_file not built (python -c 'import __graft_entry__ as g; g.build()')")
+    trace = str(tmp_path / "c_trace.csv")
+    r = subprocess.run([exe, os.path.join(HERE, "golden", "rw_ref_mixed.bin"), trace], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("file=")][0]
+    f = dict(tok.split("=", 1) for tok in line.split() if "=" in tok)
+    assert f["status"] == "solved" and f["n"] == "17" and f["solver"] == "sparse-indirect-b200-pcg"
+    import scs_python_b200 as scsb
+    data, K, stg = G.rw_problem()
+    ref = scsb.SCS(data, K, verbose=False, **stg).solve()["info"]
+    assert int(f["iter"]) == ref["iter"] and abs(float(f["pobj"]) - ref["pobj"]) <= 1e-9 * max(1.0, abs(ref["pobj"]))
+    cols, rows = _rows(trace)
+    assert len(rows) == ref["iter"] + 1 and len(cols) == 62

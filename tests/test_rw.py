@@ -148,3 +148,22 @@ def test_files_are_byte_identical_to_the_reference_library(tmp_path):
     assert open(ours, "rb").read() == open(theirs, "rb").read()
     rd, rK, rstg = scsb.read_data(theirs)
     _same_problem(data, K, stg, rd, rK, rstg)
+
+
+def test_plain_c_client_builds_and_reports_errors():
+    """tools/c/run_from_file.c compiles against include/scs_b200.h with gcc alone; without a device it reads
+    the file and then refuses to solve (no CPU fallback); a missing file is an error."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = os.path.join(ROOT, "tools", "c", "_bin", "run_from_file")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tools", "c", "run_from_file.c"), "-L" + os.path.join(ROOT, "scs_python_b200"),
+                    "-lscsb200", "-Wl,-rpath,$ORIGIN/../../../scs_python_b200", "-o", exe], check=True)
+    r = subprocess.run([exe, "/no/such/file"], capture_output=True, text=True)
+    assert r.returncode == 3
+    if B.lib.scs_b200_device_count() == 0:
+        r = subprocess.run([exe, os.path.join(HERE, "golden", "rw_ref_mixed.bin")], capture_output=True, text=True)
+        assert r.returncode == 4 and "no CPU fallback" in r.stderr
