@@ -110,15 +110,23 @@ def test_plain_c_client_runs_from_file(gpu, tmp_path):
     exe = os.path.join(os.path.dirname(HERE), "tools", "c", "_bin", "run_from_file")
     if not os.path.exists(exe):
         pytest.skip("tools/c/_bin/run_from_file not built (python -c 'import __graft_entry__ as g; g.build()')")
-    trace = str(tmp_path / "c_trace.csv")
-    r = subprocess.run([exe, os.path.join(HERE, "golden", "rw_ref_mixed.bin"), trace], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0, r.stdout + r.stderr
-    line = [ln for ln in r.stdout.splitlines() if ln.startswith("file=")][0]
-    f = dict(tok.split("=", 1) for tok in line.split() if "=" in tok)
+    golden = os.path.join(HERE, "golden", "rw_ref_mixed.bin")
+
+    def run(*extra):
+        r = subprocess.run([exe, golden, *extra], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("file=")][0]
+        return dict(tok.split("=", 1) for tok in line.split() if "=" in tok)
+    f = run()
     assert f["status"] == "solved" and f["n"] == "17" and f["solver"] == "sparse-indirect-b200-pcg"
     import scs_python_b200 as scsb
     data, K, stg = G.rw_problem()
     ref = scsb.SCS(data, K, verbose=False, **stg).solve()["info"]
     assert int(f["iter"]) == ref["iter"] and abs(float(f["pobj"]) - ref["pobj"]) <= 1e-9 * max(1.0, abs(ref["pobj"]))
+    # with a trace the residuals are refreshed every iteration, which feeds the CG tolerance rule
+    # (scs.c:703-720): a different, equally valid trajectory -- as in the reference
+    trace = str(tmp_path / "c_trace.csv")
+    g = run(trace)
     cols, rows = _rows(trace)
-    assert len(rows) == ref["iter"] + 1 and len(cols) == 62
+    assert g["status"] == "solved" and len(rows) == int(g["iter"]) + 1 and len(cols) == 62
+    assert abs(float(g["pobj"]) - ref["pobj"]) <= 1e-5 * max(1.0, abs(ref["pobj"]))
