@@ -157,7 +157,13 @@ int TiledOp::build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force) {
   const long long nnz1 = m1.nnz, nnz2 = m2 ? m2->nnz : 0, total = nnz1 + nnz2;
   nnz = total;
   if (nrows <= 0 || total <= 0 || total > 0x7fffffffLL) return 0;
-  if (!force && total < (4ll << 20)) return 0;  // small matrices: launch-latency bound, row engine is fine
+  // Small matrices are better off on the row engine: too few (row bin, column bin) cells to keep 148 CTAs
+  // busy, and two launches per product.  Measured on the LASSO family (profiles/r1w_tiled_threshold.txt):
+  // 6.6 M entries: row engine 25 % faster end to end; 26.5 M: tiled 1.3x (A) / 0.96x (A' | P); 53 M: 1.58x /
+  // 1.31x; 106 M: 1.36x / 1.36x.  SCS_B200_TILED_MIN_NNZ overrides the threshold (tests).
+  long long min_nnz = 16ll << 20;
+  if (const char *e = getenv("SCS_B200_TILED_MIN_NNZ")) min_nnz = atoll(e);
+  if (!force && total < min_nnz) return 0;
   const int nrb = (nrows + kTR - 1) / kTR;
   const int ncbA = (m1.ncols + kTC - 1) / kTC > 0 ? (m1.ncols + kTC - 1) / kTC : 1;
   const int ncbB = m2 ? (m2->ncols + kTC - 1) / kTC : 0;

@@ -123,13 +123,18 @@ def test_tiled_full_solve_matches_row_engine(scsb, monkeypatch, which):
     helpers.verify_solution(data, K, a, 1e-9, 1e-9, cone_tol=1e-6)
 
 
-def test_tiled_auto_selection_on_large_lasso(scsb):
-    """5.3 M non-zeros: above the size threshold, so the default path is the tiled engine; the result
+def test_tiled_auto_selection_on_large_lasso(scsb, monkeypatch):
+    """Automatic selection (size threshold lowered from 16 M to 1 M stored entries so that a 5.3 M instance
+    qualifies; the padding heuristic and the short-row classification run as in production): the result
     must meet the reference's convergence criteria recomputed on the host, and the engine in use is
     reported by the workspace statistics."""
     from scs_python_b200 import problems as P
     data, cone, _ = P.lasso(50_000, 100_000, 100, seed=4)
+    small = scsb.SCS(data, cone, verbose=False, max_iters=5000)
+    assert small._solver.stats()["tiled_a"] == 0            # below the production threshold: row engine
+    monkeypatch.setenv("SCS_B200_TILED_MIN_NNZ", "1000000")
     solver = scsb.SCS(data, cone, verbose=False, max_iters=5000)
+    monkeypatch.delenv("SCS_B200_TILED_MIN_NNZ")
     sol = solver.solve(warm_start=False)
     assert sol["info"]["status_val"] == 1, sol["info"]["status"]
     helpers.verify_solution(data, cone, sol, 1e-4, 1e-4, cone_tol=1e-6)
