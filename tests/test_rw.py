@@ -167,3 +167,46 @@ def test_plain_c_client_builds_and_reports_errors():
     if B.lib.scs_b200_device_count() == 0:
         r = subprocess.run([exe, os.path.join(HERE, "golden", "rw_ref_mixed.bin")], capture_output=True, text=True)
         assert r.returncode == 4 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.parametrize("name", ["random_prob", "mpc_bug1", "mpc_bug2", "mpc_bug3"])
+def test_upstream_fixture_files(name):
+    """The reference's own data files (S/test/problems/, written by older SCS versions with other integer
+    widths): this reader must return what the reference's reader returned when tests/golden/kat.json was made
+    (make_golden.py read_file_problems).  Runs where /root/reference is mounted (the build container)."""
+    path = os.path.join("/root/reference/scs_source/test/problems", name)
+    if not os.path.exists(path):
+        pytest.skip("/root/reference not on this box")
+    from tests import helpers
+    rec = [p for p in helpers.golden("kat.json")["file_problems"] if p["name"] == name][0]
+    rd, rK, rstg = scsb.read_data(path)
+    assert rd["A"].shape == (rec["m"], rec["n"])
+    assert np.array_equal(rd["A"].data, np.array(rec["Ax"], float)) and list(rd["A"].indices) == rec["Ai"]
+    assert list(rd["A"].indptr) == rec["Ap"]
+    assert np.array_equal(rd["b"], np.array(rec["b"], float)) and np.array_equal(rd["c"], np.array(rec["c"], float))
+    if rec.get("Px") is not None:
+        assert np.array_equal(rd["P"].data, np.array(rec["Px"], float)) and list(rd["P"].indices) == rec["Pi"]
+    else:
+        assert rd["P"] is None
+    kc = rec["cone"]
+    for key in ("z", "l", "ep", "ed"):
+        assert rK.get(key, 0) == kc.get(key, 0)
+    for key in ("q", "s"):
+        assert list(rK.get(key, [])) == list(kc.get(key, []))
+    assert np.array_equal(np.asarray(rK.get("p", []), float), np.asarray(kc.get("p", []), float))
+
+
+def test_older_file_with_a_shorter_settings_block(tmp_path):
+    """Files of older versions end before the newest settings fields (S/test/problems/random_prob, written by
+    3.0.0, is 20 bytes short).  The reference keeps reading, reports the short reads and leaves those fields
+    zero (rw.c:60-72, 159-180); its own tests then solve the problem.  Same here -- while a file that ends
+    inside the cone or data block stays an error (test_read_errors)."""
+    data, K, stg = G.rw_problem()
+    path = str(tmp_path / "prob.bin")
+    scsb.write_data(path, data, K, **stg)
+    raw = open(path, "rb").read()
+    open(path, "wb").write(raw[:-20])     # drops acceleration_regularization, _relaxation (f64) and adaptive_scale (i32)
+    rd, rK, rstg = scsb.read_data(path)
+    assert np.array_equal(rd["b"], data["b"]) and rK["l"] == K["l"]
+    assert rstg["acceleration_regularization"] == 0.0 and rstg["acceleration_relaxation"] == 0.0
+    assert rstg["adaptive_scale"] is False and rstg["acceleration_type_1"] == 1 and rstg["max_iters"] == stg["max_iters"]
