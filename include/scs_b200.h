@@ -268,6 +268,15 @@ double scs_b200_bench_spmv(ScsWork *w, scs_int which, scs_int reps, double *alg_
  * count (0 when the operator runs on the row engine). */
 scs_int scs_b200_tiled_profile(ScsWork *w, scs_int which, double *out, scs_int cap);
 
+/* Host-only test hook: the work plan of the tiled SpMV engine for a synthetic cell map (no device needed).
+ * hg[rb * ncb + cb] = groups of the (row bin, column bin) cell, p1 / p2 = row pointers (p2 may be NULL).
+ * items_out: 5 ints per item {cta, row bin, slot, first index into seq_out, one past the last};
+ * binfo_out: 2 ints per row bin {first slot, pieces}; cost_out: modelled cost per CTA.  Returns the number
+ * of items, -1 when a buffer is too small. */
+scs_int scs_b200_tiled_plan(scs_int nrows, scs_int ncb, const scs_int *hg, const scs_int *p1, const scs_int *p2,
+                            scs_int sms, scs_int *items_out, scs_int items_cap, scs_int *seq_out, scs_int seq_cap,
+                            scs_int *binfo_out, double *cost_out, scs_int *ncta_out, scs_int *nseq_out);
+
 /* Iteration marks: the next scs_solve records a CUDA event on the workspace stream at the
  * top of ADMM iteration `begin_iter` and of `end_iter` (or at loop exit if earlier), and
  * switches per-launch event timing of the SpMV kernels on between them. */

@@ -172,6 +172,9 @@ lib.scs_b200_free_data.restype = None
 lib.scs_b200_free_data.argtypes = [C.POINTER(ScsData), C.POINTER(ScsCone), C.POINTER(ScsSettings)]
 lib.scs_b200_csv_header.restype = C.c_char_p
 lib.scs_b200_csv_header.argtypes = []
+lib.scs_b200_tiled_plan.restype = c_int
+lib.scs_b200_tiled_plan.argtypes = [c_int, c_int, p_int, p_int, p_int, c_int, p_int, c_int, p_int, c_int, p_int, p_double,
+                                    p_int, p_int]
 lib.scs_b200_tiled_profile.restype = c_int
 lib.scs_b200_tiled_profile.argtypes = [C.c_void_p, c_int, p_double, c_int]
 lib.scs_b200_solve_batch.restype = c_int

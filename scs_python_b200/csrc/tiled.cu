@@ -144,6 +144,151 @@ bool force_tiled_only() {
 
 }  // namespace
 
+// Host plan of a tiled operator (no device work): which row bins are tiled, how their (row bin, active
+// column bin) cells are cut into one contiguous, cost-balanced range per CTA, and where every piece parks
+// its partial sums.  hg[rb * ncb + cb] = groups of the cell (summed over the warps), p1 / p2 = row pointers
+// of the source matrices (p2 may be null).
+void tiled_plan_host(int nrows, int ncb, const int *hg, const int *p1, const int *p2, int sms, bool tiled_only,
+                     TiledPlan &P) {
+  const int nrb = (nrows + kTR - 1) / kTR;
+  struct Atom { int rb, cell; double cost; };  // one active column bin of a tiled row bin
+  std::vector<std::vector<int>> act((size_t)nrb);
+  std::vector<Atom> atoms;
+  std::vector<char> is_direct((size_t)nrb, 0);
+  const double kCellFixed = 8.0 * kTC, kSlot = 12.0, kItemFixed = 16.0 * kTR, kCellFloor = 70000.0;
+  for (int rb = 0; rb < nrb; ++rb) {
+    const int r0 = rb * kTR, r1 = std::min(nrows, r0 + kTR);
+    long long bn = 0;
+    int maxlen = 0;
+    for (int r = r0; r < r1; ++r) {
+      const int len = (p1[r + 1] - p1[r]) + (p2 ? p2[r + 1] - p2[r] : 0);
+      bn += len;
+      maxlen = std::max(maxlen, len);
+    }
+    if (bn == 0 || (!tiled_only && bn <= 6ll * (r1 - r0) && maxlen <= 32)) {
+      is_direct[rb] = 1;
+      continue;
+    }
+    for (int cb = 0; cb < ncb; ++cb)
+      if (hg[(size_t)rb * ncb + cb] > 0) act[rb].push_back(cb);
+    const int na = (int)act[rb].size();
+    for (int a = 0; a < na; ++a) {
+      // a column bin costs its stream + its x-slice, and never less than the latency of one slice hand-over
+      double cst = std::max(kSlot * 32.0 * hg[(size_t)rb * ncb + act[rb][a]] + kCellFixed, kCellFloor);
+      atoms.push_back(Atom{rb, a, cst});
+    }
+  }
+  double ctot = 0.0;
+  for (const Atom &a : atoms) ctot += a.cost;
+  const int natoms = (int)atoms.size();
+  const int ncta = std::max(1, std::min(sms, natoms));
+  // cut points: atoms [cut[b], cut[b+1]) go to CTA b
+  std::vector<int> cut((size_t)ncta + 1, natoms);
+  cut[0] = 0;
+  {
+    double run = 0.0;
+    int b = 1;
+    for (int i = 0; i < natoms && b < ncta; ++i) {
+      run += atoms[i].cost;
+      while (b < ncta && run >= ctot * b / ncta) cut[b++] = i + 1;
+    }
+    // snap a cut that would leave a sliver of a row bin (fewer than 3 cells) to the bin boundary
+    for (int b2 = 1; b2 < ncta; ++b2) {
+      int k = cut[b2];
+      if (k <= 0 || k >= natoms || atoms[k - 1].rb != atoms[k].rb) continue;
+      int first = k, last = k;
+      while (first > 0 && atoms[first - 1].rb == atoms[k].rb) --first;
+      while (last < natoms && atoms[last].rb == atoms[k].rb) ++last;
+      if (k - first < 3) k = first;
+      else if (last - k < 3) k = last;
+      cut[b2] = std::max(k, cut[b2 - 1]);
+    }
+    for (int b2 = 1; b2 <= ncta; ++b2) cut[b2] = std::max(cut[b2], cut[b2 - 1]);
+  }
+  // items: maximal runs of one row bin inside a CTA's range
+  std::vector<HostItem> items;
+  std::vector<std::vector<int>> mine((size_t)ncta);
+  std::vector<int> pieces_of((size_t)nrb, 0);
+  for (int b = 0; b < ncta; ++b) {
+    int i = cut[b];
+    while (i < cut[b + 1]) {
+      int j = i + 1;
+      while (j < cut[b + 1] && atoms[j].rb == atoms[i].rb) ++j;
+      HostItem hi;
+      hi.rb = atoms[i].rb; hi.first = atoms[i].cell; hi.last = atoms[j - 1].cell + 1;
+      hi.piece = pieces_of[hi.rb]++;
+      hi.cost = kItemFixed;
+      for (int k = i; k < j; ++k) hi.cost += atoms[k].cost;
+      mine[b].push_back((int)items.size());
+      items.push_back(hi);
+      i = j;
+    }
+  }
+  int pslots = 0;
+  int pieces_max = 1;
+  std::vector<int2> h_binfo((size_t)nrb);
+  for (int rb = 0; rb < nrb; ++rb) {
+    h_binfo[rb] = make_int2(pslots, pieces_of[rb]);  // pieces == 0: short-row bin (or no rows at all)
+    pslots += pieces_of[rb];
+    pieces_max = std::max(pieces_max, pieces_of[rb]);
+  }
+  const int nitems = (int)items.size();
+  P.cta_cost.assign((size_t)ncta, 0.0);
+  P.cta_items.assign((size_t)ncta, 0);
+  for (int b = 0; b < ncta; ++b) {
+    for (int i : mine[b]) P.cta_cost[b] += items[i].cost;
+    P.cta_items[b] = (int)mine[b].size();
+  }
+  std::vector<TItem> &h_items = P.items;
+  std::vector<int> &h_cta_off = P.cta_off, &h_seq = P.seq, &h_seq_off = P.seq_off;
+  h_items.clear(); h_seq.clear();
+  h_cta_off.assign(1, 0); h_seq_off.assign(1, 0);
+  for (int b = 0; b < ncta; ++b) {
+    for (int i : mine[b]) {
+      const HostItem &hi = items[i];
+      TItem t;
+      t.rb = hi.rb;
+      t.slot = h_binfo[hi.rb].x + hi.piece;
+      t.a0 = (int)h_seq.size();
+      for (int a = hi.first; a < hi.last; ++a) h_seq.push_back(act[hi.rb][a]);
+      t.a1 = (int)h_seq.size();
+      h_items.push_back(t);
+    }
+    h_cta_off.push_back((int)h_items.size());
+    h_seq_off.push_back((int)h_seq.size());
+  }
+  const int nitems_total = (int)P.items.size();
+  (void)nitems_total;
+  P.ncta = ncta; P.pslots = pslots; P.pieces_max = pieces_max;
+  P.binfo = h_binfo;
+  P.ndirect = (int)std::count(is_direct.begin(), is_direct.end(), (char)1);
+}
+
+// test hook (host only): the plan for a synthetic cell map.  items_out: 5 ints per item {cta, row bin, slot,
+// first index into seq_out, one past the last}; binfo_out: 2 ints per row bin {first slot, pieces};
+// cost_out: one double per CTA.  Returns the number of items, or -1 when a buffer is too small; *ncta_out
+// and *nseq_out receive the CTA and sequence counts.
+extern "C" scs_int scs_b200_tiled_plan(scs_int nrows, scs_int ncb, const scs_int *hg, const scs_int *p1, const scs_int *p2,
+                                       scs_int sms, scs_int *items_out, scs_int items_cap, scs_int *seq_out, scs_int seq_cap,
+                                       scs_int *binfo_out, double *cost_out, scs_int *ncta_out, scs_int *nseq_out) {
+  if (nrows <= 0 || ncb <= 0 || !hg || !p1 || sms <= 0 || !items_out || !seq_out || !binfo_out || !cost_out) return -1;
+  TiledPlan P;
+  tiled_plan_host(nrows, ncb, hg, p1, p2, sms, false, P);
+  const int nitems = (int)P.items.size(), nrb = (nrows + kTR - 1) / kTR;
+  if (nitems > items_cap || (int)P.seq.size() > seq_cap) return -1;
+  for (int b = 0; b < P.ncta; ++b)
+    for (int i = P.cta_off[b]; i < P.cta_off[b + 1]; ++i) {
+      items_out[5 * i + 0] = b; items_out[5 * i + 1] = P.items[i].rb; items_out[5 * i + 2] = P.items[i].slot;
+      items_out[5 * i + 3] = P.items[i].a0; items_out[5 * i + 4] = P.items[i].a1;
+    }
+  for (size_t k = 0; k < P.seq.size(); ++k) seq_out[k] = P.seq[k];
+  for (int rb = 0; rb < nrb; ++rb) { binfo_out[2 * rb] = P.binfo[rb].x; binfo_out[2 * rb + 1] = P.binfo[rb].y; }
+  for (int b = 0; b < P.ncta; ++b) cost_out[b] = P.cta_cost[b];
+  if (ncta_out) *ncta_out = P.ncta;
+  if (nseq_out) *nseq_out = (int)P.seq.size();
+  return nitems;
+}
+
 void TiledOp::destroy() {
   dev_free(d.items); dev_free(d.cta_off); dev_free(d.seq); dev_free(d.cta_seq_off); dev_free(d.gbase);
   dev_free(d.pk); dev_free(d.val); dev_free(d.partial); dev_free(d.binfo); dev_free(d.prof);
@@ -236,111 +381,16 @@ int TiledOp::build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force) {
       if (cudaMemcpyAsync(p2.data(), m2->ptr, sizeof(int) * p2.size(), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) break;
-    struct Atom { int rb, cell; double cost; };  // one active column bin of a tiled row bin
-    std::vector<std::vector<int>> act((size_t)nrb);
-    std::vector<Atom> atoms;
-    std::vector<char> is_direct((size_t)nrb, 0);
-    const double kCellFixed = 8.0 * kTC, kSlot = 12.0, kItemFixed = 16.0 * kTR, kCellFloor = 70000.0;
-    for (int rb = 0; rb < nrb; ++rb) {
-      const int r0 = rb * kTR, r1 = std::min(nrows, r0 + kTR);
-      long long bn = 0;
-      int maxlen = 0;
-      for (int r = r0; r < r1; ++r) {
-        const int len = (p1[r + 1] - p1[r]) + (m2 ? p2[r + 1] - p2[r] : 0);
-        bn += len;
-        maxlen = std::max(maxlen, len);
-      }
-      if (bn == 0 || (!force_tiled_only() && bn <= 6ll * (r1 - r0) && maxlen <= 32)) {
-        is_direct[rb] = 1;
-        continue;
-      }
-      for (int cb = 0; cb < ncb; ++cb)
-        if (hg[(size_t)rb * ncb + cb] > 0) act[rb].push_back(cb);
-      const int na = (int)act[rb].size();
-      for (int a = 0; a < na; ++a) {
-        // a column bin costs its stream + its x-slice, and never less than the latency of one slice hand-over
-        double cst = std::max(kSlot * 32.0 * hg[(size_t)rb * ncb + act[rb][a]] + kCellFixed, kCellFloor);
-        atoms.push_back(Atom{rb, a, cst});
-      }
-    }
-    double ctot = 0.0;
-    for (const Atom &a : atoms) ctot += a.cost;
-    const int natoms = (int)atoms.size();
-    const int ncta = std::max(1, std::min(c.sms, natoms));
-    // cut points: atoms [cut[b], cut[b+1]) go to CTA b
-    std::vector<int> cut((size_t)ncta + 1, natoms);
-    cut[0] = 0;
-    {
-      double run = 0.0;
-      int b = 1;
-      for (int i = 0; i < natoms && b < ncta; ++i) {
-        run += atoms[i].cost;
-        while (b < ncta && run >= ctot * b / ncta) cut[b++] = i + 1;
-      }
-      // snap a cut that would leave a sliver of a row bin (fewer than 3 cells) to the bin boundary
-      for (int b2 = 1; b2 < ncta; ++b2) {
-        int k = cut[b2];
-        if (k <= 0 || k >= natoms || atoms[k - 1].rb != atoms[k].rb) continue;
-        int first = k, last = k;
-        while (first > 0 && atoms[first - 1].rb == atoms[k].rb) --first;
-        while (last < natoms && atoms[last].rb == atoms[k].rb) ++last;
-        if (k - first < 3) k = first;
-        else if (last - k < 3) k = last;
-        cut[b2] = std::max(k, cut[b2 - 1]);
-      }
-      for (int b2 = 1; b2 <= ncta; ++b2) cut[b2] = std::max(cut[b2], cut[b2 - 1]);
-    }
-    // items: maximal runs of one row bin inside a CTA's range
-    std::vector<HostItem> items;
-    std::vector<std::vector<int>> mine((size_t)ncta);
-    std::vector<int> pieces_of((size_t)nrb, 0);
-    for (int b = 0; b < ncta; ++b) {
-      int i = cut[b];
-      while (i < cut[b + 1]) {
-        int j = i + 1;
-        while (j < cut[b + 1] && atoms[j].rb == atoms[i].rb) ++j;
-        HostItem hi;
-        hi.rb = atoms[i].rb; hi.first = atoms[i].cell; hi.last = atoms[j - 1].cell + 1;
-        hi.piece = pieces_of[hi.rb]++;
-        hi.cost = kItemFixed;
-        for (int k = i; k < j; ++k) hi.cost += atoms[k].cost;
-        mine[b].push_back((int)items.size());
-        items.push_back(hi);
-        i = j;
-      }
-    }
-    int pslots = 0;
-    pieces_max = 1;
-    std::vector<int2> h_binfo((size_t)nrb);
-    for (int rb = 0; rb < nrb; ++rb) {
-      h_binfo[rb] = make_int2(pslots, pieces_of[rb]);  // pieces == 0: short-row bin (or no rows at all)
-      pslots += pieces_of[rb];
-      pieces_max = std::max(pieces_max, pieces_of[rb]);
-    }
-    const int nitems = (int)items.size();
+    TiledPlan plan;
+    tiled_plan_host(nrows, ncb, hg.data(), p1.data(), m2 ? p2.data() : nullptr, c.sms, force_tiled_only(), plan);
+    const std::vector<TItem> &h_items = plan.items;
+    const std::vector<int> &h_cta_off = plan.cta_off, &h_seq = plan.seq, &h_seq_off = plan.seq_off;
+    const std::vector<int2> &h_binfo = plan.binfo;
+    const int ncta = plan.ncta, pslots = plan.pslots, nitems = (int)h_items.size();
+    pieces_max = plan.pieces_max;
     has_tiled = nitems > 0;
-    cta_cost.assign((size_t)ncta, 0.0);
-    cta_items.assign((size_t)ncta, 0);
-    for (int b = 0; b < ncta; ++b) {
-      for (int i : mine[b]) cta_cost[b] += items[i].cost;
-      cta_items[b] = (int)mine[b].size();
-    }
-    std::vector<TItem> h_items;
-    std::vector<int> h_cta_off(1, 0), h_seq, h_seq_off(1, 0);
-    for (int b = 0; b < ncta; ++b) {
-      for (int i : mine[b]) {
-        const HostItem &hi = items[i];
-        TItem t;
-        t.rb = hi.rb;
-        t.slot = h_binfo[hi.rb].x + hi.piece;
-        t.a0 = (int)h_seq.size();
-        for (int a = hi.first; a < hi.last; ++a) h_seq.push_back(act[hi.rb][a]);
-        t.a1 = (int)h_seq.size();
-        h_items.push_back(t);
-      }
-      h_cta_off.push_back((int)h_items.size());
-      h_seq_off.push_back((int)h_seq.size());
-    }
+    cta_cost = plan.cta_cost;
+    cta_items = plan.cta_items;
     if (dev_alloc(&d.items, h_items.size()) || dev_alloc(&d.cta_off, h_cta_off.size()) ||
         dev_alloc(&d.seq, h_seq.size()) || dev_alloc(&d.cta_seq_off, h_seq_off.size()) ||
         dev_alloc(&d.partial, (size_t)std::max(pslots, 1) * kTR) || dev_alloc(&d.binfo, (size_t)nrb) ||
@@ -356,8 +406,7 @@ int TiledOp::build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force) {
     lap("plan+upload");
     if (verbose)
       fprintf(stderr, "tiled build: rows %d nnz %lld slots %lld (x%.3f) row bins %d col bins %d items %d ctas %d max pieces %d direct bins %d\n",
-              nrows, total, slots, (double)slots / (double)total, nrb, ncb, nitems, ncta, pieces_max,
-              (int)std::count(is_direct.begin(), is_direct.end(), (char)1));
+              nrows, total, slots, (double)slots / (double)total, nrb, ncb, nitems, ncta, pieces_max, plan.ndirect);
     d.nrows = nrows; d.nrb = nrb; d.ncb = ncb; d.ncbA = ncbA;
     d.len1 = m1.ncols; d.len2 = m2 ? m2->ncols : 0;
     d.nitems = nitems; d.ncta = ncta;

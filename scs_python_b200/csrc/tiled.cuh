@@ -91,6 +91,17 @@ struct TiledOp {
   int build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force);
   void destroy();
 };
+// host plan of a tiled operator (tiled.cu: tiled_plan_host), separated from the device work for the CPU tests
+struct TiledPlan {
+  int ncta = 1, pslots = 0, pieces_max = 1, ndirect = 0;
+  std::vector<TItem> items;               // grouped by CTA
+  std::vector<int> cta_off, seq, seq_off; // as in TiledDev
+  std::vector<int2> binfo;
+  std::vector<double> cta_cost;
+  std::vector<int> cta_items;
+};
+void tiled_plan_host(int nrows, int ncb, const int *hg, const int *p1, const int *p2, int sms, bool tiled_only,
+                     TiledPlan &P);
 // SCS_B200_TILED: "0" never, "1" whenever the structure allows, unset: size / padding heuristic
 int tiled_env_mode();
 

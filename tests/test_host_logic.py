@@ -216,3 +216,80 @@ def test_solve_batch_wrapper_fills_the_c_structures(monkeypatch):
         B.solve_batch([prepared[0][:8] + (np.zeros(2), prepared[0][9])], verbose=False)   # c of the wrong length
     with pytest.raises(TypeError):
         B.solve_batch([prepared[0][:1] + (np.zeros(3, dtype=np.int32),) + prepared[0][2:]], verbose=False)  # Ax not float
+
+
+# ------------------------------------------------------------ tiled SpMV engine: the host plan ------
+TR, TC = 16384, 4096   # csrc/tiled.cuh: rows per row bin, columns per column bin
+
+
+def _tiled_plan(nrows, hg, p1, p2, sms):
+    from scs_python_b200 import _scs_b200 as B
+    nrb, ncb = hg.shape
+    hg = np.ascontiguousarray(hg, dtype=np.int32)
+    p1 = np.ascontiguousarray(p1, dtype=np.int32)
+    p2c = np.ascontiguousarray(p2, dtype=np.int32) if p2 is not None else None
+    cap = int(nrb * ncb + nrb + sms + 8)
+    items, seq = np.zeros(5 * cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+    binfo, cost = np.zeros(2 * nrb, dtype=np.int32), np.zeros(sms)
+    ncta, nseq = B.c_int(0), B.c_int(0)
+    import ctypes as C
+    n = B.lib.scs_b200_tiled_plan(nrows, ncb, B._iptr(hg), B._iptr(p1), B._iptr(p2c) if p2c is not None else None, sms,
+                                  B._iptr(items), cap, B._iptr(seq), cap, B._iptr(binfo), B._dptr(cost),
+                                  C.byref(ncta), C.byref(nseq))
+    assert n >= 0
+    return items[:5 * n].reshape(-1, 5), seq[:nseq.value], binfo.reshape(-1, 2), cost[:ncta.value]
+
+
+@pytest.mark.parametrize("seed,nrb,ncb,sms", [(0, 9, 40, 148), (1, 3, 7, 148), (2, 30, 25, 16), (3, 1, 1, 148), (4, 6, 300, 148)])
+def test_tiled_plan_covers_every_cell_once_and_balances(seed, nrb, ncb, sms):
+    """Invariants of the partition the streaming kernel relies on (csrc/tiled.cu: tiled_plan_host): every active
+    cell of every tiled row bin is visited exactly once, in ascending column order inside a piece; the pieces
+    of a row bin own consecutive scratch slots in piece order (the epilogue adds them in that order); short-row
+    and empty bins get no item; CTA ranges are contiguous in (row bin, column) order; the modelled cost of the
+    busiest CTA is within one cell (+ the snapping slack of two cells) of the mean."""
+    rng = np.random.RandomState(seed)
+    nrows = nrb * TR - (rng.randint(1, TR) if nrb > 1 else TR - 5000)
+    kind = rng.randint(0, 3, size=nrb)                 # 0: heavy rows, 1: short rows (direct bin), 2: empty
+    if nrb > 1:
+        kind[0] = 0
+    rowlen = np.zeros(nrows, dtype=np.int64)
+    hg = np.zeros((nrb, ncb), dtype=np.int32)
+    for rb in range(nrb):
+        r0, r1 = rb * TR, min(nrows, (rb + 1) * TR)
+        if kind[rb] == 0:
+            rowlen[r0:r1] = rng.randint(20, 60, size=r1 - r0)
+            active = rng.rand(ncb) < 0.7
+            active[rng.randint(ncb)] = True
+            hg[rb, active] = rng.randint(16, 200, size=int(active.sum()))
+        elif kind[rb] == 1:
+            rowlen[r0:r1] = rng.randint(0, 3, size=r1 - r0)
+            hg[rb, rng.randint(ncb)] = 16          # cells exist in the format but must not be scheduled
+    p1 = np.concatenate([[0], np.cumsum(rowlen)])
+    items, seq, binfo, cost = _tiled_plan(nrows, hg, p1, None, sms)
+    tiled_bins = [rb for rb in range(nrb) if kind[rb] == 0]
+    # coverage, order, slots
+    seen = {rb: [] for rb in tiled_bins}
+    pieces = {rb: [] for rb in tiled_bins}
+    prev_key = (-1, -1)
+    assert list(items[:, 0]) == sorted(items[:, 0]) and (len(items) == 0 or items[:, 0].max() < len(cost) <= sms)
+    for cta, rb, slot, a0, a1 in items:
+        assert rb in seen, "a short-row / empty bin was scheduled"
+        cells = list(seq[a0:a1])
+        assert cells == sorted(cells) and len(set(cells)) == len(cells) and len(cells) > 0
+        assert (rb, cells[0]) > prev_key                 # contiguous ranges in (row bin, column) order
+        prev_key = (rb, cells[-1])
+        seen[rb] += cells
+        pieces[rb].append(slot)
+    for rb in tiled_bins:
+        assert seen[rb] == [cb for cb in range(ncb) if hg[rb, cb] > 0]
+        assert binfo[rb, 1] == len(pieces[rb]) and pieces[rb] == list(range(binfo[rb, 0], binfo[rb, 0] + binfo[rb, 1]))
+    for rb in range(nrb):
+        if kind[rb] != 0:
+            assert binfo[rb, 1] == 0
+    slots = sorted(s for rb in tiled_bins for s in pieces[rb])
+    assert slots == list(range(len(slots)))              # scratch slots are dense and unique
+    # balance (cost model of tiled_plan_host: max(384 g + 32768, 70000) per cell, 262144 per item)
+    if len(items):
+        cell = np.maximum(384.0 * hg[hg > 0] + 8.0 * TC, 70000.0)
+        assert abs(cost.sum() - (cell[np.isin(np.nonzero(hg)[0], tiled_bins)].sum() + 16.0 * TR * len(items))) < 1e-6 * cost.sum()
+        assert cost.max() <= cost.sum() / len(cost) + 3 * cell.max() + 2 * 16.0 * TR * max(1, items.shape[0] // len(cost) + 1)
