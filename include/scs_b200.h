@@ -297,14 +297,24 @@ scs_int scs_b200_get_marks(const ScsWork *w, ScsB200Marks *out);
  * One process per GPU.  Rank 0 obtains an id with scs_b200_dist_unique_id (128 bytes), every
  * rank calls scs_b200_dist_init(rank, world, id) after scs_b200_set_device and before
  * scs_init.  Workspaces created afterwards take the FULL problem on every rank, keep a
- * cone-aligned block of rows of A, and return the full (x, y, s).  Collectives: NCCL sum
- * all-reduces of n-vectors (A_g' z_g, once per CG iteration) and of a few reduction scalars. */
+ * cone-aligned block of rows of A and the columns those rows touch (columns touched by one rank only
+ * are private to it, the others are replicated), and return the full (x, y, s).  Collectives per CG
+ * iteration: one NCCL sum all-reduce of the shared block of A_g' z_g with the scalar p'Gp riding along, and
+ * one gather of two reduction scalars; a few scalar gathers per ADMM iteration; Anderson acceleration
+ * gathers one (mem x (2 mem + 1)) trapezoid per rank.  world == 1 with SCS_B200_DIST_SELFTEST=1 in the
+ * environment runs the same code path on one GPU (collectives degenerate to copies). */
 scs_int scs_b200_dist_unique_id(void *out128);
 scs_int scs_b200_dist_init(scs_int rank, scs_int world, const void *id128);
 void scs_b200_dist_finalize(void);
 /* host-only: the block rank `rank` of `world` would own: out = {row0, m_local, nnz_local, z, l,
  * bsize, qsize, ssize, cssize, ep, ed, psize} */
 scs_int scs_b200_dist_partition(const ScsData *d, const ScsCone *k, scs_int rank, scs_int world, scs_int out[12]);
+/* host-only: the local problem rank `rank` of `world` would build.  sizes = {row0, m_loc, n_shared, n_loc,
+ * nnz(A_loc), nnz(P_loc)}; the local column order is [shared columns (replicated) | columns private to the
+ * rank], loc2glob maps it back.  Array pointers may be NULL (a first call then only returns the sizes). */
+scs_int scs_b200_dist_local(const ScsData *d, const ScsCone *k, scs_int rank, scs_int world, scs_int sizes[6],
+                            scs_int *loc2glob, scs_int *Ap, scs_int *Ai, scs_float *Ax, scs_int *Pp, scs_int *Pi,
+                            scs_float *Px, scs_float *c_loc);
 scs_int scs_b200_dist_rank(void);
 scs_int scs_b200_dist_world(void);
 

@@ -127,6 +127,9 @@ lib.scs_b200_dist_rank.restype = c_int
 lib.scs_b200_dist_world.restype = c_int
 lib.scs_b200_dist_partition.restype = c_int
 lib.scs_b200_dist_partition.argtypes = [C.POINTER(ScsData), C.POINTER(ScsCone), c_int, c_int, C.POINTER(c_int * 12)]
+lib.scs_b200_dist_local.restype = c_int
+lib.scs_b200_dist_local.argtypes = [C.POINTER(ScsData), C.POINTER(ScsCone), c_int, c_int, C.POINTER(c_int * 6), p_int,
+                                    p_int, p_int, p_double, p_int, p_int, p_double, p_double]
 lib.scs_b200_lin_sys_cg_its.restype = c_int
 lib.scs_b200_lin_sys_cg_its.argtypes = [C.c_void_p]
 lib.scs_b200_init_cone.restype = C.c_void_p
@@ -219,6 +222,41 @@ def dist_partition(shape, Ax, Ai, Ap, b, c, cone, rank, world):
         raise ValueError("partition failed")
     keys = ("row0", "m", "nnz", "z", "l", "bsize", "qsize", "ssize", "cssize", "ep", "ed", "psize")
     return dict(zip(keys, list(out)))
+
+
+def dist_local(shape, Ax, Ai, Ap, Px, Pi, Pp, b, c, cone, rank, world):
+    """Host-only: the local problem rank `rank` of `world` builds in the row-partitioned mode (same arguments as
+    SCS.__init__).  Returns dict(row0, m, n_sh, loc2glob, A=(Ax, Ai, Ap) local CSC of shape (m, n_loc),
+    P=(Px, Pi, Pp) or None, c)."""
+    import scipy.sparse as sp
+    m, n = int(shape[0]), int(shape[1])
+    Ax = _check_float_1d(Ax, "Ax"); Ai = _check_int_1d(Ai, "Ai"); Ap = _check_int_1d(Ap, "Ap")
+    b = _check_float_1d(b, "b"); c = _check_float_1d(c, "c")
+    A = make_matrix(Ax, Ai, Ap, m, n)
+    P = None
+    if Px is not None:
+        Px = _check_float_1d(Px, "Px"); Pi = _check_int_1d(Pi, "Pi"); Pp = _check_int_1d(Pp, "Pp")
+        P = make_matrix(Px, Pi, Pp, n, n)
+    k, keep = make_cone(cone)
+    d = ScsData(m, n, C.pointer(A), C.pointer(P) if P is not None else None, _dptr(b), _dptr(c))
+    sizes = (c_int * 6)()
+    nul_i, nul_d = C.cast(None, p_int), C.cast(None, p_double)
+    if lib.scs_b200_dist_local(C.byref(d), C.byref(k), int(rank), int(world), C.byref(sizes), nul_i, nul_i, nul_i, nul_d,
+                               nul_i, nul_i, nul_d, nul_d) != 0:
+        raise ValueError("partition failed")
+    row0, ml, nsh, nl, nzA, nzP = list(sizes)
+    l2g = np.zeros(nl, dtype=np.int32)
+    lAp = np.zeros(nl + 1, dtype=np.int32); lAi = np.zeros(max(nzA, 1), dtype=np.int32); lAx = np.zeros(max(nzA, 1))
+    lPp = np.zeros(nl + 1, dtype=np.int32); lPi = np.zeros(max(nzP, 1), dtype=np.int32); lPx = np.zeros(max(nzP, 1))
+    cl = np.zeros(nl)
+    if lib.scs_b200_dist_local(C.byref(d), C.byref(k), int(rank), int(world), C.byref(sizes), _iptr(l2g), _iptr(lAp),
+                               _iptr(lAi), _dptr(lAx), _iptr(lPp), _iptr(lPi), _dptr(lPx), _dptr(cl)) != 0:
+        raise ValueError("partition failed")
+    out = dict(row0=row0, m=ml, n_sh=nsh, loc2glob=l2g, c=cl,
+               A=sp.csc_matrix((lAx[:nzA], lAi[:nzA], lAp), shape=(ml, nl)), P=None)
+    if P is not None:
+        out["P"] = sp.csc_matrix((lPx[:nzP], lPi[:nzP], lPp), shape=(nl, nl))
+    return out
 
 
 def version():
@@ -449,15 +487,39 @@ def read_data(filename):
 
 def write_data(filename, shape, Ax, Ai, Ap, Px, Pi, Pp, b, c, cone, **settings):
     """SCS(write_data), S/src/rw.c:240-260, without creating a workspace (no device needed)."""
-    m, n = shape
+    m, n = int(shape[0]), int(shape[1])
+    if m <= 0 or n <= 0:
+        raise ValueError("m and n must be positive integers")
+    # same dtype / shape validation as SCS.__init__ (scsobject.h:507-640): the converted arrays are kept
+    # alive until the call returns, so the C side never sees a reinterpreted buffer
+    Ax = _check_float_1d(Ax, "Ax")
+    Ai = _check_int_1d(Ai, "Ai")
+    Ap = _check_int_1d(Ap, "Ap")
+    if len(Ap) != n + 1:
+        raise ValueError("Ap has incompatible dimension with A")
+    if len(Ai) != len(Ax) or (len(Ap) and int(Ap[-1]) != len(Ax)):
+        raise ValueError("Ai / Ax have incompatible dimension with Ap")
     A = make_matrix(Ax, Ai, Ap, m, n)
     data = ScsData()
     data.m, data.n = m, n
     data.A = C.pointer(A)
     P = None
-    if Px is not None:
+    if Px is not None and Pi is not None and Pp is not None:
+        Px = _check_float_1d(Px, "Px")
+        Pi = _check_int_1d(Pi, "Pi")
+        Pp = _check_int_1d(Pp, "Pp")
+        if len(Pp) != n + 1:
+            raise ValueError("Pp has incompatible dimension with P")
+        if len(Pi) != len(Px) or int(Pp[-1]) != len(Px):
+            raise ValueError("Pi / Px have incompatible dimension with Pp")
         P = make_matrix(Px, Pi, Pp, n, n)
         data.P = C.pointer(P)
+    b = _check_float_1d(b, "b")
+    c = _check_float_1d(c, "c")
+    if b.shape[0] != m:
+        raise ValueError("b has incompatible dimension with A")
+    if c.shape[0] != n:
+        raise ValueError("c has incompatible dimension with A")
     data.b, data.c = _dptr(b), _dptr(c)
     k, keep = make_cone(cone)
     st, keep2 = make_settings(dict(settings, write_data_filename=os.fspath(filename)))

@@ -1,6 +1,7 @@
 // aa.cu -- Anderson acceleration kernels (see aa.cuh for the design).
 #include "aa.cuh"
 #include "aa_small.cuh"
+#include "dist.cuh"
 
 namespace b200 {
 
@@ -14,13 +15,74 @@ static inline AaParams params_of(const AaDev &a) {
   p.max_weight_norm = a.max_weight_norm;
   p.x = a.x; p.f = a.f; p.g = a.g; p.g_prev = a.g_prev; p.Y = a.Y; p.S = a.S; p.D = a.D; p.x_work = a.x_work;
   p.Rpart = a.Rpart; p.st = a.st;
+  p.cnt_lo = a.cnt_lo; p.cnt_hi = a.cnt_hi;
   return p;
 }
 
 
+// finalisers of the reducing kernels below (functors: in the row-partitioned mode they run after the
+// ranks' raw sums have been gathered, common.cuh grid_reduce_fin / dist.cuh dist_finish)
+struct FinAaUpdate {
+  AaState *st;
+  int mem, min_len;
+  __device__ __forceinline__ void operator()(double *o, DevScalars *) const {
+    const int it = st->iter;
+    st->success = 0;
+    st->aa_norm = 0.0;
+    st->do_solve = 0;
+    if (it == 0) {
+      st->iter = 1;
+    } else {
+      const int idx = (it - 1) % mem;
+      st->nrm_s_col[idx] = sqrt(o[0]);
+      st->nrm_y_col[idx] = sqrt(o[1]);
+      st->norm_g = sqrt(o[2]);
+      st->len = it < mem ? it : mem;
+      if (it >= min_len) st->do_solve = 1;  // iter++ happens after the solve
+      else st->iter = it + 1;
+    }
+  }
+};
+struct FinAaApply {
+  AaState *st;
+  double *vnorm2_out;
+  __device__ __forceinline__ void operator()(double *o, DevScalars *) const {
+    if (st->do_solve && st->success && vnorm2_out) *vnorm2_out = o[0];
+  }
+};
+struct FinAaSafeguard {
+  AaState *st;
+  int mem;
+  double safeguard_factor;
+  int *rej_cnt, *acc_cnt;
+  __device__ __forceinline__ void operator()(double *o, DevScalars *) const {
+    if (!(st->aa_norm > 0.0) || !st->success) return;  // the kernel did not reduce anything (see its early exits)
+    st->success = 0;
+    const double nd = sqrt(o[0]);
+    if (nd > safeguard_factor * st->norm_g) {
+      st->sg_reject = 1;
+      st->n_safeguard_reject++;
+      aa_reset_dev(st, mem);
+      if (rej_cnt) *rej_cnt += 1;
+    } else {
+      st->sg_reject = 0;
+      if (acc_cnt) *acc_cnt += 1;
+    }
+  }
+};
+struct FinAaRollback {
+  AaState *st;
+  double *vnorm2_out;
+  __device__ __forceinline__ void operator()(double *o, DevScalars *) const {
+    if (!st->sg_reject) return;
+    st->sg_reject = 0;
+    if (vnorm2_out) *vnorm2_out = o[0];
+  }
+};
+
 // init_accel_params (aa.c:310-324) when iter == 0, else update_accel_params (aa.c:340-390)
 __global__ void __launch_bounds__(kThreads)
-k_aa_update(AaParams a, const double *__restrict__ xin, const double *__restrict__ fin, RedWs ws) {
+k_aa_update(AaParams a, const double *__restrict__ xin, const double *__restrict__ fin, RedWs ws, DevScalars *S) {
   AaState *st = a.st;
   const int it = st->iter;
   double v[3] = {0.0, 0.0, 0.0};
@@ -38,25 +100,10 @@ k_aa_update(AaParams a, const double *__restrict__ xin, const double *__restrict
       a.S[col + j] = s; a.D[col + j] = d; a.Y[col + j] = y; a.g[j] = gj;
       a.x[j] = xj; a.f[j] = fj; a.g_prev[j] = gj;
       if (a.x_work) a.x_work[j] = xj;
-      v[0] = fma(s, s, v[0]); v[1] = fma(y, y, v[1]); v[2] = fma(gj, gj, v[2]);
+      if (j >= a.cnt_lo && j < a.cnt_hi) { v[0] = fma(s, s, v[0]); v[1] = fma(y, y, v[1]); v[2] = fma(gj, gj, v[2]); }
     }
   }
-  grid_reduce<3, 0>(v, ws, [st, a, it](double *o) {
-    st->success = 0;
-    st->aa_norm = 0.0;
-    st->do_solve = 0;
-    if (it == 0) {
-      st->iter = 1;
-    } else {
-      const int idx = (it - 1) % a.mem;
-      st->nrm_s_col[idx] = sqrt(o[0]);
-      st->nrm_y_col[idx] = sqrt(o[1]);
-      st->norm_g = sqrt(o[2]);
-      st->len = it < a.mem ? it : a.mem;
-      if (it >= a.min_len) st->do_solve = 1;  // iter++ happens after the solve
-      else st->iter = it + 1;
-    }
-  });
+  grid_reduce_fin<3, 0>(v, ws, S, FinAaUpdate{st, a.mem, a.min_len});
 }
 
 // One column step set of the Householder elimination of the stacked [R; B] block: B is
@@ -131,11 +178,12 @@ __global__ void __launch_bounds__(kAaT) k_aa_tsqr1(AaParams a) {
   for (int k = t; k < a.mem * Cmax; k += kAaT) sm.R[k] = 0.0;
   __syncthreads();
   const double *Asrc = a.type1 ? a.S : a.Y;
-  const int ntiles = (a.dim + kAaT - 1) / kAaT;
+  const int dimc = a.cnt_hi - a.cnt_lo;  // rows this rank counts
+  const int ntiles = (dimc + kAaT - 1) / kAaT;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int row = tile * kAaT + t;
-    const bool valid = row < a.dim;
-    const int rows = (a.dim - tile * kAaT) < kAaT ? (a.dim - tile * kAaT) : kAaT;
+    const int row = a.cnt_lo + tile * kAaT + t;
+    const bool valid = row < a.cnt_hi;
+    const int rows = (dimc - tile * kAaT) < kAaT ? (dimc - tile * kAaT) : kAaT;
     for (int cidx = 0; cidx < C; ++cidx) {
       double val = 0.0;
       if (valid) {
@@ -153,7 +201,10 @@ __global__ void __launch_bounds__(kAaT) k_aa_tsqr1(AaParams a) {
 }
 
 
-__global__ void __launch_bounds__(kAaT) k_aa_tsqr2(AaParams a, int nblk) {
+// Merge `nblk` trapezoids read from `src` ([blk][mem][Cmax] slots, rows packed with stride C).  merge_out ==
+// null: add the sqrt(r) I rows and solve (the final stage).  Otherwise (row-partitioned mode): write the merged
+// trapezoid of this rank to merge_out and stop; the ranks' trapezoids are gathered and merged by a second call.
+__global__ void __launch_bounds__(kAaT) k_aa_tsqr2(AaParams a, const double *__restrict__ src, int nblk, double *merge_out) {
   extern __shared__ double smem[];
   __shared__ double sh_sqrt_r, sh_r;
   AaState *st = a.st;
@@ -186,7 +237,7 @@ __global__ void __launch_bounds__(kAaT) k_aa_tsqr2(AaParams a, int nblk) {
   for (int k = t; k < a.mem * Cmax; k += kAaT) sm.R[k] = 0.0;
   __syncthreads();
   const double sqrt_r = sh_sqrt_r;
-  const int nrows = nblk * len + len;
+  const int nrows = nblk * len + (merge_out ? 0 : len);
   for (int base = 0; base < nrows; base += kAaT) {
     const int rho = base + t;
     const bool valid = rho < nrows;
@@ -196,7 +247,7 @@ __global__ void __launch_bounds__(kAaT) k_aa_tsqr2(AaParams a, int nblk) {
       if (valid) {
         if (rho < nblk * len) {
           const int blk = rho / len, i = rho % len;
-          val = a.Rpart[(size_t)blk * a.mem * Cmax + (size_t)i * C + cidx];
+          val = src[(size_t)blk * a.mem * Cmax + (size_t)i * C + cidx];
         } else {
           const int ar = rho - nblk * len;  // row of [sqrt(r) I | sqrt(r) I | 0]
           if (cidx == ar || (a.type1 && cidx == len + ar)) val = sqrt_r;
@@ -207,12 +258,16 @@ __global__ void __launch_bounds__(kAaT) k_aa_tsqr2(AaParams a, int nblk) {
     __syncthreads();
     tile_eliminate(sm.B, rows, sm.R, len, C, sm.red, sm.sig, sm.coef);
   }
+  if (merge_out) {
+    for (int k = t; k < len * C; k += kAaT) merge_out[k] = sm.R[k];
+    return;
+  }
   if (t == 0) aa_small_solve(a, sm.R, len, C, sh_r, sm.B);
 }
 
 // f -= D gamma (+ relaxation, aa.c:393-408,640-647); refresh sum f^2
 __global__ void __launch_bounds__(kThreads)
-k_aa_apply(AaParams a, double *__restrict__ f, double *vnorm2_out, RedWs ws) {
+k_aa_apply(AaParams a, double *__restrict__ f, double *vnorm2_out, RedWs ws, DevScalars *S) {
   AaState *st = a.st;
   if (!st->do_solve || !st->success) return;
   const int len = st->len;
@@ -230,17 +285,15 @@ k_aa_apply(AaParams a, double *__restrict__ f, double *vnorm2_out, RedWs ws) {
       fj = a.relaxation * fj + (1.0 - a.relaxation) * xw;
     }
     f[j] = fj;
-    v[0] = fma(fj, fj, v[0]);
+    if (j >= a.cnt_lo && j < a.cnt_hi) v[0] = fma(fj, fj, v[0]);
   }
-  grid_reduce<1, 0>(v, ws, [vnorm2_out](double *o) {
-    if (vnorm2_out) *vnorm2_out = o[0];
-  });
+  grid_reduce_fin<1, 0>(v, ws, S, FinAaApply{st, vnorm2_out});
 }
 
 // aa_safeguard, aa.c:856-901 (decision part)
 __global__ void __launch_bounds__(kThreads)
 k_aa_safeguard(AaParams a, const double *__restrict__ f_new, const double *__restrict__ x_new, int *rej_cnt,
-               int *acc_cnt, RedWs ws) {
+               int *acc_cnt, RedWs ws, DevScalars *S) {
   AaState *st = a.st;
   if (!(st->aa_norm > 0.0)) return;  // scs.c:1386 gate
   if (!st->success) {                // aa.c:867-871: nothing to check -> counts as accepted
@@ -250,26 +303,15 @@ k_aa_safeguard(AaParams a, const double *__restrict__ f_new, const double *__res
   double v[1] = {0.0};
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < a.dim; j += gridDim.x * blockDim.x) {
     const double d = x_new[j] - f_new[j];
-    v[0] = fma(d, d, v[0]);
+    if (j >= a.cnt_lo && j < a.cnt_hi) v[0] = fma(d, d, v[0]);
   }
-  grid_reduce<1, 0>(v, ws, [st, a, rej_cnt, acc_cnt](double *o) {
-    st->success = 0;
-    const double nd = sqrt(o[0]);
-    if (nd > a.safeguard_factor * st->norm_g) {
-      st->sg_reject = 1;
-      st->n_safeguard_reject++;
-      aa_reset_dev(st, a.mem);
-      if (rej_cnt) *rej_cnt += 1;
-    } else {
-      st->sg_reject = 0;
-      if (acc_cnt) *acc_cnt += 1;
-    }
-  });
+  grid_reduce_fin<1, 0>(v, ws, S, FinAaSafeguard{st, a.mem, a.safeguard_factor, rej_cnt, acc_cnt});
 }
 
 // roll back to the last un-accelerated pair when the safeguard rejected (aa.c:886-897)
 __global__ void __launch_bounds__(kThreads)
-k_aa_rollback(AaParams a, double *__restrict__ f_new, double *__restrict__ x_new, double *vnorm2_out, RedWs ws) {
+k_aa_rollback(AaParams a, double *__restrict__ f_new, double *__restrict__ x_new, double *vnorm2_out, RedWs ws,
+              DevScalars *S) {
   AaState *st = a.st;
   if (!st->sg_reject) return;
   double v[1] = {0.0};
@@ -277,12 +319,9 @@ k_aa_rollback(AaParams a, double *__restrict__ f_new, double *__restrict__ x_new
     const double fj = a.f[j];
     f_new[j] = fj;
     x_new[j] = a.x[j];
-    v[0] = fma(fj, fj, v[0]);
+    if (j >= a.cnt_lo && j < a.cnt_hi) v[0] = fma(fj, fj, v[0]);
   }
-  grid_reduce<1, 0>(v, ws, [st, vnorm2_out](double *o) {
-    st->sg_reject = 0;
-    if (vnorm2_out) *vnorm2_out = o[0];
-  });
+  grid_reduce_fin<1, 0>(v, ws, S, FinAaRollback{st, vnorm2_out});
 }
 
 __global__ void k_aa_reset(AaState *st, int mem) {
@@ -304,6 +343,7 @@ int AaDev::init(Ctx *ctx, int dim_, int mem_, int min_len_, int type1_, double r
     return -1;
   }
   dim = dim_; mem = mem_clamped; type1 = type1_ ? 1 : 0;
+  cnt_lo = 0; cnt_hi = dim_;
   min_len = mem > 0 ? (min_len_ < mem ? min_len_ : mem) : 0;
   regularization = reg; relaxation = relax; safeguard_factor = sgf; max_weight_norm = mwn; ir_max_steps = irs;
   CUDA_OK(cudaSetDevice(c->device));
@@ -324,6 +364,9 @@ int AaDev::init(Ctx *ctx, int dim_, int mem_, int min_len_, int type1_, double r
   if (nblk < 1) nblk = 1;
   const int Cmax = 2 * mem + 1;
   if (dev_alloc_zero(&Rpart, (size_t)nblk * mem * Cmax, c->stream)) return -1;
+  if (c->dist && (dev_alloc_zero(&Rsend, (size_t)c->world * mem * Cmax, c->stream) ||
+                  dev_alloc_zero(&Rrecv, (size_t)c->world * mem * Cmax, c->stream)))
+    return -1;
   smem1 = smem2 = aa_smem_bytes(mem);
   const size_t scratch = sizeof(double) * (size_t)(4 * mem * mem + 5 * mem + 8);
   if ((size_t)Cmax * kAaT * sizeof(double) < scratch) {
@@ -339,7 +382,7 @@ void AaDev::destroy() {
   if (!c) return;
   cudaSetDevice(c->device);
   dev_free(x); dev_free(f); dev_free(g); dev_free(g_prev); dev_free(Y); dev_free(S); dev_free(D);
-  dev_free(x_work); dev_free(Rpart); dev_free(st);
+  dev_free(x_work); dev_free(Rpart); dev_free(st); dev_free(Rsend); dev_free(Rrecv);
   if (st_host) cudaFreeHost(st_host);
   st_host = nullptr;
 }
@@ -349,10 +392,20 @@ int AaDev::apply(double *fv, const double *xv, double *vnorm2_out) {
   AaParams p = params_of(*this);
   const int grid = c->grid_ew();
   cudaStream_t s = c->stream;
-  k_aa_update<<<grid, kThreads, 0, s>>>(p, xv, fv, c->red);
+  k_aa_update<<<grid, kThreads, 0, s>>>(p, xv, fv, c->red, c->S);
+  if (dist_finish(*c, 3, 0, FinAaUpdate{st, mem, min_len})) return -1;
   k_aa_tsqr1<<<nblk, kAaT, smem1, s>>>(p);
-  k_aa_tsqr2<<<1, kAaT, smem2, s>>>(p, nblk);
-  k_aa_apply<<<grid, kThreads, 0, s>>>(p, fv, vnorm2_out, c->red);
+  if (c->dist) {  // this rank's trapezoid -> gather -> final merge over the ranks, identical on every rank
+    const size_t slot = (size_t)mem * (2 * mem + 1);
+    k_aa_tsqr2<<<1, kAaT, smem2, s>>>(p, Rpart, nblk, Rsend + (size_t)c->rank * slot);
+    if (dist_allreduce_oop(*c, Rsend, Rrecv, (size_t)c->world * slot)) return -1;
+    k_aa_tsqr2<<<1, kAaT, smem2, s>>>(p, Rrecv, c->world, nullptr);
+    c->launches++;
+  } else {
+    k_aa_tsqr2<<<1, kAaT, smem2, s>>>(p, Rpart, nblk, nullptr);
+  }
+  k_aa_apply<<<grid, kThreads, 0, s>>>(p, fv, vnorm2_out, c->red, c->S);
+  if (dist_finish(*c, 1, 0, FinAaApply{st, vnorm2_out})) return -1;
   c->launches += 4;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -362,10 +415,18 @@ int AaDev::safeguard(double *f_new, double *x_new, double *vnorm2_out, int *rej_
   if (mem <= 0) return 0;
   AaParams p = params_of(*this);
   const int grid = c->grid_ew();
-  k_aa_safeguard<<<grid, kThreads, 0, c->stream>>>(p, f_new, x_new, rej_cnt, acc_cnt, c->red);
-  k_aa_rollback<<<grid, kThreads, 0, c->stream>>>(p, f_new, x_new, vnorm2_out, c->red);
+  k_aa_safeguard<<<grid, kThreads, 0, c->stream>>>(p, f_new, x_new, rej_cnt, acc_cnt, c->red, c->S);
+  if (dist_finish(*c, 1, 0, FinAaSafeguard{st, mem, safeguard_factor, rej_cnt, acc_cnt})) return -1;
+  k_aa_rollback<<<grid, kThreads, 0, c->stream>>>(p, f_new, x_new, vnorm2_out, c->red, c->S);
+  if (dist_finish(*c, 1, 0, FinAaRollback{st, vnorm2_out})) return -1;
   c->launches += 2;
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int AaDev::set_counted_rows(int lo, int hi) {
+  if (lo < 0 || hi > dim || hi <= lo) return -1;
+  cnt_lo = lo; cnt_hi = hi;
   return 0;
 }
 

@@ -35,6 +35,11 @@ struct AaDev {
   double *Y = nullptr, *S = nullptr, *D = nullptr, *x_work = nullptr;
   double *Rpart = nullptr;  // [nblk][mem][C] per-CTA trapezoids
   int nblk = 0;
+  // row-partitioned mode (dist.cuh): rows this rank counts, and the per-rank trapezoids that are gathered
+  // (sum all-reduce of a buffer in which every rank fills its own slot) before the final merge
+  int cnt_lo = 0, cnt_hi = 0;
+  double *Rsend = nullptr, *Rrecv = nullptr;  // [world][mem][Cmax]
+  int set_counted_rows(int lo, int hi);
   AaState *st = nullptr;       // device
   AaState *st_host = nullptr;  // pinned
   size_t smem1 = 0, smem2 = 0;

@@ -11,6 +11,9 @@ struct AaParams {  // by-value kernel argument
   double regularization, relaxation, safeguard_factor, max_weight_norm;
   double *x, *f, *g, *g_prev, *Y, *S, *D, *x_work, *Rpart;
   AaState *st;
+  // row-partitioned mode: inner products / norms / the TSQR run over the rows [cnt_lo, cnt_hi) this rank
+  // counts (the replicated shared block and tau belong to rank 0); [0, dim) everywhere else
+  int cnt_lo, cnt_hi;
 };
 
 static __device__ __forceinline__ void aa_reset_dev(AaState *st, int mem) {  // aa_reset, aa.c:934-964

@@ -21,6 +21,7 @@ namespace b200 {
 constexpr int kThreads = 256;    // CTA size of every streaming kernel
 constexpr int kMaxRedVals = 24;  // max simultaneous reduction outputs of one kernel
 constexpr int kCtasPerSm = 8;    // resident 256-thread CTAs per SM (2048 threads / SM)
+constexpr int kMaxWorld = 16;    // ranks of a row-partitioned solve (one box: 8)
 
 #define B200_PRINTF(...)          \
   do {                            \
@@ -88,12 +89,18 @@ struct DevScalars {
   // in-region device timing of the two CG SpMV kernels (bench marks): [0] z = R_y^-1 A p,
   // [1] Gp = A'z + P p + R_x p.  Start = first CTA's first instruction, end = last CTA done.
   int kt_on;
-  // row-partitioned mode: 1 => grid reductions park their raw sums / maxes in part[] and the
-  // consuming formula runs in k_apply_fin after the NCCL all-reduce (see dist_finish)
+  // row-partitioned mode: 1 => grid reductions park their raw sums / maxes in this rank's slot of
+  // gsend[] and the consuming formula runs in k_apply_fin after ONE sum all-reduce gsend -> grecv
+  // (every rank only ever writes its own slot, so the sum is a gather; the finaliser then combines the
+  // ranks' values in rank order: bit-identical scalars on every rank, sums and maxes in one collective)
   int dist;
+  int dist_rank, dist_world;
+  int pad1;
   unsigned int kt_ticket[2], kt_cnt[2];
   unsigned long long kt_start[2], kt_ns[2];
   double part[kMaxRedVals];
+  double pGp_local;  // row-partitioned CG: (A_g p)' R_y^-1 (A_g p) of the local rows, see linsys.cu
+  double gsend[kMaxWorld * kMaxRedVals], grecv[kMaxWorld * kMaxRedVals];
 };
 
 // indices into DevScalars::res
@@ -111,6 +118,9 @@ struct Ctx {
   int device = 0;
   int sms = 148;
   bool dist = false;  // workspace of a row-partitioned solve (dist.cuh)
+  int rank = 0, world = 1;
+  int n_sh = 0;    // shared (replicated) columns: the prefix [0, n_sh) of every local n-vector
+  int cnt_lo = 0;  // reductions over n-space count [cnt_lo, n): 0 on rank 0, n_sh on the others
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   RedWs red{nullptr, nullptr, 0};
@@ -312,16 +322,33 @@ template <int NS, int NM, class Fin>
 __device__ __forceinline__ void grid_reduce_fin(double *vals, const RedWs &ws, DevScalars *S, Fin fin) {
   grid_reduce<NS, NM>(vals, ws, [S, fin](double *o) {
     if (S->dist) {
+      double *slot = S->gsend + S->dist_rank * (NS + NM);
 #pragma unroll
-      for (int k = 0; k < NS + NM; ++k) S->part[k] = o[k];
+      for (int k = 0; k < NS + NM; ++k) slot[k] = o[k];
     } else {
       fin(o, S);
     }
   });
 }
+// after the all-reduce gsend -> grecv: combine the ranks' raw values in rank order, run the formula, and
+// clear this rank's slot (slots are laid out with the stride of the current reduction, so a stale value
+// would land in another rank's slot of a later, wider reduction)
 template <class Fin>
-__global__ void k_apply_fin(Fin fin, DevScalars *S) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) fin(S->part, S);
+__global__ void k_apply_fin(Fin fin, DevScalars *S, int ns, int nm) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int nv = ns + nm, world = S->dist_world;
+  double o[kMaxRedVals];
+  for (int k = 0; k < nv; ++k) {
+    double v = (k < ns) ? 0.0 : -INFINITY;
+    for (int r = 0; r < world; ++r) {
+      const double pv = S->grecv[r * nv + k];
+      v = (k < ns) ? (v + pv) : fmax(v, pv);
+    }
+    o[k] = v;
+  }
+  double *slot = S->gsend + S->dist_rank * nv;
+  for (int k = 0; k < nv; ++k) slot[k] = 0.0;
+  fin(o, S);
 }
 #endif  // __CUDACC__
 

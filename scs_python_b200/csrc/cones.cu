@@ -936,6 +936,23 @@ int ConeDev::init(Ctx *ctx, const ScsCone *k, int m_) {
     psd_small_max_d = psd_large_max_d = 0;
     for (const PsdEntry &e : small) psd_small_max_d = e.d > psd_small_max_d ? e.d : psd_small_max_d;
     for (const PsdEntry &e : large) psd_large_max_d = e.d > psd_large_max_d ? e.d : psd_large_max_d;
+    {  // launch geometry of the two Jacobi launches: maxima over the cones each one covers
+      const size_t budget = (size_t)200 * 1024;
+      auto geom = [&](const std::vector<PsdEntry> &v, int ctas, size_t &smem, int &warps) {
+        smem = 0; warps = 1;
+        for (const PsdEntry &e : v) {
+          if (e.s < 2) continue;
+          const int NB = psd_num_blocks(e.d, ctas, budget);
+          const int nb = (e.d + NB - 1) / NB;
+          const size_t sm = (size_t)32 * nb * e.d;
+          smem = sm > smem ? sm : smem;
+          const int w = nb < 1 ? 1 : (nb > kPsdJacMaxWarps ? kPsdJacMaxWarps : nb);  // nloc / 2 pairs per local round
+          warps = w > warps ? w : warps;
+        }
+      };
+      geom(small, 1, psd_small_smem, psd_small_warps);
+      geom(large, kPsdCluster, psd_large_smem, psd_large_warps);
+    }
     ents = small;
     ents.insert(ents.end(), large.begin(), large.end());
     psd_tiles = (psd_max_d + kGT - 1) / kGT;
@@ -1015,20 +1032,13 @@ int ConeDev::project_nonlinear(double *x, const double *sv, const double *r) {
     k_psd_prep<<<n_psd, kPsdPrepThreads, 0, st>>>(x, sv, r, psd, psd_state, psd_W, psd_G, psd_V);
     k_psd_gemm_wv<<<gtiles, 256, 0, st>>>(psd, psd_state, psd_W, psd_V, psd_G, psd_tiles);
     c->launches += 2;
-    // shared memory: two blocks of (G, V) columns per CTA
+    // shared memory: two blocks of (G, V) columns per CTA.  Every cone of a launch recomputes its own
+    // block count from its own d inside the kernel, and the footprint 32 nb(d) d is not monotone in d
+    // (s = [225, 201]: 165600 vs 167232 bytes), so the launch is sized by the maximum over the cones it
+    // covers, not by the largest d.
     const size_t budget = (size_t)200 * 1024;
-    auto smem_for = [&](int max_d, int ctas) {
-      const int NB = psd_num_blocks(max_d, ctas, budget);
-      const int nb = (max_d + NB - 1) / NB;
-      return (size_t)32 * nb * max_d;
-    };
-    auto threads_for = [&](int max_d, int ctas) {
-      const int NB = psd_num_blocks(max_d, ctas, budget);
-      const int nb = (max_d + NB - 1) / NB;
-      int w = nb;  // nloc / 2 pairs per local round
-      w = w < 1 ? 1 : (w > kPsdJacMaxWarps ? kPsdJacMaxWarps : w);
-      return 32 * w;
-    };
+    auto smem_for = [&](int, int ctas) { return ctas == 1 ? psd_small_smem : psd_large_smem; };
+    auto threads_for = [&](int, int ctas) { return 32 * (ctas == 1 ? psd_small_warps : psd_large_warps); };
     if (n_psd_small > 0) {
       const size_t sm = smem_for(psd_small_max_d, 1);
       k_psd_jacobi<1><<<n_psd_small, threads_for(psd_small_max_d, 1), sm, st>>>(psd, psd_state, 0, psd_G, psd_V, budget);

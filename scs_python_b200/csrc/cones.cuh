@@ -51,6 +51,8 @@ struct ConeDev {
   PsdState *psd_state = nullptr;
   int psd_tiles = 0;    // ceil(psd_max_d / 64)
   int psd_small_max_d = 0, psd_large_max_d = 0;
+  size_t psd_small_smem = 0, psd_large_smem = 0;  // dynamic shared memory of the two Jacobi launches (max over their cones)
+  int psd_small_warps = 1, psd_large_warps = 1;
   double *d_bu = nullptr, *d_bl = nullptr, *box_t = nullptr;
   double *d_p = nullptr;
   int *bnd_off = nullptr, *bnd_len = nullptr;  // cones of size > 1 for enforce_cone_boundaries

@@ -63,6 +63,22 @@ int dist_allreduce(Ctx &c, double *buf, size_t count, int op) {
   return 0;
 }
 
+int dist_allreduce_oop(Ctx &c, const double *send, double *recv, size_t count) {
+  if (count == 0) return 0;
+  if (!g_dist.on()) {  // world == 1 (self-test of the partitioned code path on one GPU)
+    if (cudaMemcpyAsync(recv, send, count * sizeof(double), cudaMemcpyDeviceToDevice, c.stream) != cudaSuccess) return -1;
+    return 0;
+  }
+  const int rc = g_nccl.all_reduce(send, recv, count, kNcclFloat64, kNcclSum, g_dist.comm, c.stream);
+  if (rc != 0) {
+    fprintf(stderr, "libscsb200: ncclAllReduce failed: %s\n", g_nccl.error_string ? g_nccl.error_string(rc) : "?");
+    return -1;
+  }
+  c.collectives++;
+  c.collective_bytes += (long long)(count * sizeof(double));
+  return 0;
+}
+
 int current_device();
 
 }  // namespace b200
@@ -80,7 +96,12 @@ extern "C" scs_int scs_b200_dist_unique_id(void *out128) {
 extern "C" scs_int scs_b200_dist_init(scs_int rank, scs_int world, const void *id128) {
   if (world < 1 || rank < 0 || rank >= world) return -1;
   if (g_dist.comm) return -1;  // already initialised
-  if (world == 1) { g_dist.rank = 0; g_dist.world = 1; return 0; }
+  if (world == 1) {
+    g_dist.rank = 0; g_dist.world = 1;
+    const char *e = getenv("SCS_B200_DIST_SELFTEST");
+    g_dist.selftest = e && *e && atoi(e) != 0;
+    return 0;
+  }
   if (!id128 || !g_nccl.load()) return -1;
   if (cudaSetDevice(current_device()) != cudaSuccess) return -1;
   NcclUniqueId id;

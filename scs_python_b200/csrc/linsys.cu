@@ -33,6 +33,75 @@ struct EpiScaleRy {
   __device__ __forceinline__ void apply(State &, int i, double acc, const Pre &q) const { out[i] = acc / q.ry; }
   __device__ __forceinline__ void finish(State &, const RedWs &, DevScalars *S) const { kt_end_ticket(S, 0); }
 };
+// Row-partitioned CG: out[i] = (A_g x)_i / R_y,i and the local part of p'Gp that lives in m-space,
+// (A_g p)' R_y^-1 (A_g p) = sum_i out_i (A_g p)_i  ->  S->pGp_local (no collective: it rides on the
+// all-reduce of A_g' z_g, see LinSys::launch_G)
+struct EpiScaleRyDot {
+  static constexpr bool kSeparate = false;
+  struct State { double dot; };
+  double *out;
+  const double *ry;
+  DevScalars *S_;
+  int kt_cont = 0;
+  __device__ __forceinline__ void row2(State &, int, double, double) const {}
+  __device__ __forceinline__ void init(State &s) const { s.dot = 0.0; if (!kt_cont) kt_begin(S_, 0); }
+  __device__ __forceinline__ void row(State &s, int i, double acc) const {
+    const double o = acc / ry[i];
+    out[i] = o;
+    s.dot = fma(o, acc, s.dot);
+  }
+  struct Pre { double ry; };
+  __device__ __forceinline__ Pre load(int i) const { return Pre{ry[i]}; }
+  __device__ __forceinline__ void apply(State &s, int i, double acc, const Pre &q) const {
+    const double o = acc / q.ry;
+    out[i] = o;
+    s.dot = fma(o, acc, s.dot);
+  }
+  __device__ __forceinline__ void finish(State &s, const RedWs &ws, DevScalars *S) const {
+    double v[1] = {s.dot};
+    grid_reduce<1, 0>(v, ws, [S](double *o) {
+      S->pGp_local = o[0];
+      kt_end_last(S, 0);
+    });
+  }
+};
+// Row-partitioned CG: pp_j = (P p)_j + R_x,j p_j over the local columns, and this rank's whole
+// contribution to p'Gp: pGp_local + sum over the columns it counts of p_j pp_j, written to *slot (the
+// scalar that is all-reduced together with the shared block of A_g' z_g)
+struct EpiPP {
+  static constexpr bool kSeparate = false;
+  struct State { double dot; };
+  double *pp;
+  const double *p, *rx;
+  double *slot;
+  int cnt_lo;
+  __device__ __forceinline__ void row2(State &, int, double, double) const {}
+  __device__ __forceinline__ void init(State &s) const { s.dot = 0.0; }
+  __device__ __forceinline__ void row(State &s, int j, double acc) const {
+    const double pj = p[j];
+    const double g = acc + rx[j] * pj;
+    pp[j] = g;
+    if (j >= cnt_lo) s.dot = fma(pj, g, s.dot);
+  }
+  __device__ __forceinline__ void finish(State &s, const RedWs &ws, DevScalars *S) const {
+    double v[1] = {s.dot};
+    double *sl = slot;
+    grid_reduce<1, 0>(v, ws, [S, sl](double *o) { *sl = S->pGp_local + o[0]; });
+  }
+};
+// y[row] = acc, usable by both engines (the tiled epilogue pass needs load / apply)
+struct EpiStoreT : EpiNoState {
+  double *y;
+  DevScalars *S_;
+  int kt_cat = -1;  // timing category closed by this product (-1: none)
+  int kt_cont = 0;
+  __device__ __forceinline__ void init(State &) const { if (kt_cat >= 0 && !kt_cont) kt_begin(S_, kt_cat); }
+  __device__ __forceinline__ void row(State &, int r, double acc) const { y[r] = acc; }
+  struct Pre {};
+  __device__ __forceinline__ Pre load(int) const { return Pre{}; }
+  __device__ __forceinline__ void apply(State &, int r, double acc, const Pre &) const { y[r] = acc; }
+  __device__ __forceinline__ void finish(State &, const RedWs &, DevScalars *S) const { if (kt_cat >= 0) kt_end_ticket(S, kt_cat); }
+};
 // Gp_j = (A' z)_j + (P p)_j + R_x,j p_j ; p'Gp ; alpha = z'r / p'Gp     (private.c:181-183)
 struct EpiG {
   static constexpr bool kSeparate = false;
@@ -67,6 +136,33 @@ struct EpiG {
     });
   }
 };
+// start of CG: z'r and ||r||_inf are in, decide whether to iterate at all (private.c:170-174)
+struct FinCgStart {
+  CgCtl ctl;
+  __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    S->ztr = o[0];
+    S->norm_r = o[1];
+    const int done = (o[1] < fmax(S->cg_tol, 1e-12)) ? 1 : 0;
+    S->cg_done = done;
+    cg_set_loop(ctl, !done);
+  }
+};
+// one CG step done: beta, the stop test (private.c:189-213)
+struct FinCgUpdate {
+  CgCtl ctl;
+  __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    const double ztr_prev = S->ztr;
+    const int its = S->cg_its + 1;
+    S->cg_its = its;
+    S->cg_its_total += 1;
+    S->norm_r = o[1];
+    S->ztr = o[0];
+    S->beta = o[0] / ztr_prev;
+    const int done = (o[1] < S->cg_tol || ztr_prev == 0.0 || !(o[1] == o[1]) || its >= S->cg_max_its) ? 1 : 0;
+    if (done) S->cg_done = 1;
+    cg_set_loop(ctl, !done);
+  }
+};
 // warm-started start of CG: r = b - G s ; x = s ; z = M r ; p = z ; z'r ; ||r||_inf
 //                                                       (private.c:153-174)
 struct EpiG0 {
@@ -78,6 +174,7 @@ struct EpiG0 {
   double *r, *z, *p;
   CgCtl ctl;
   const double *extra;  // row-partitioned mode: all-reduced A' R_y^-1 A s (may alias r), else null
+  int cnt_lo = 0;       // row-partitioned mode: z'r counts the columns >= cnt_lo (shared block on rank 0 only)
   int kt_cont = 0;      // (set by tiled_launch; this epilogue carries no timing hooks)
   __device__ __forceinline__ void init(State &st) const { st.ztr = 0.0; st.nr = 0.0; }
   __device__ __forceinline__ void row(State &st, int j, double acc) const {
@@ -89,7 +186,7 @@ struct EpiG0 {
     r[j] = rj;
     z[j] = zj;
     p[j] = zj;
-    st.ztr = fma(zj, rj, st.ztr);
+    if (j >= cnt_lo) st.ztr = fma(zj, rj, st.ztr);
     st.nr = fmax(st.nr, fabs(rj));
   }
   struct Pre { double b, s, rx, M; };
@@ -106,14 +203,7 @@ struct EpiG0 {
   }
   __device__ __forceinline__ void finish(State &st, const RedWs &ws, DevScalars *S) const {
     double v[2] = {st.ztr, st.nr};
-    const CgCtl cc = ctl;
-    grid_reduce<1, 1>(v, ws, [S, cc](double *o) {
-      S->ztr = o[0];
-      S->norm_r = o[1];
-      const int done = (o[1] < fmax(S->cg_tol, 1e-12)) ? 1 : 0;
-      S->cg_done = done;
-      cg_set_loop(cc, !done);
-    });
+    grid_reduce_fin<1, 1>(v, ws, S, FinCgStart{ctl});
   }
 };
 // y_i = ((A x)_i - ry_i) / R_y,i   written over ry      (private.c:304-309)
@@ -145,7 +235,7 @@ k_scale_ry(const double *__restrict__ by, const double *__restrict__ ry, double 
 // cold start of CG (s == NULL): r = b ; x = 0 ; z = M r ; p = z      (private.c:147-152,170-174)
 __global__ void __launch_bounds__(kThreads)
 k_cg_init_cold(double *__restrict__ b, const double *__restrict__ M, double *__restrict__ r,
-               double *__restrict__ z, double *__restrict__ p, int n, RedWs ws, DevScalars *S, CgCtl ctl) {
+               double *__restrict__ z, double *__restrict__ p, int n, int cnt_lo, RedWs ws, DevScalars *S, CgCtl ctl) {
   if (S->cg_done) return;
   double v[2] = {0.0, 0.0};
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -155,16 +245,10 @@ k_cg_init_cold(double *__restrict__ b, const double *__restrict__ M, double *__r
     r[j] = rj;
     z[j] = zj;
     p[j] = zj;
-    v[0] = fma(zj, rj, v[0]);
+    if (j >= cnt_lo) v[0] = fma(zj, rj, v[0]);
     v[1] = fmax(v[1], fabs(rj));
   }
-  grid_reduce<1, 1>(v, ws, [S, ctl](double *o) {
-    S->ztr = o[0];
-    S->norm_r = o[1];
-    const int done = (o[1] < fmax(S->cg_tol, 1e-12)) ? 1 : 0;
-    S->cg_done = done;
-    cg_set_loop(ctl, !done);
-  });
+  grid_reduce_fin<1, 1>(v, ws, S, FinCgStart{ctl});
 }
 
 // x += alpha p ; r -= alpha Gp ; z = M r ; z'r ; ||r||_inf ; stop test ; beta
@@ -184,18 +268,48 @@ k_cg_update(double *__restrict__ x, double *__restrict__ r, double *__restrict__
     v[0] = fma(zj, rj, v[0]);
     v[1] = fmax(v[1], fabs(rj));
   }
-  grid_reduce<1, 1>(v, ws, [S, ctl](double *o) {
-    const double ztr_prev = S->ztr;
-    const int its = S->cg_its + 1;
-    S->cg_its = its;
-    S->cg_its_total += 1;
-    S->norm_r = o[1];
-    S->ztr = o[0];
-    S->beta = o[0] / ztr_prev;
-    const int done = (o[1] < S->cg_tol || ztr_prev == 0.0 || !(o[1] == o[1]) || its >= S->cg_max_its) ? 1 : 0;
-    if (done) S->cg_done = 1;
-    cg_set_loop(ctl, !done);
-  });
+  grid_reduce_fin<1, 1>(v, ws, S, FinCgUpdate{ctl});
+}
+
+// the same step of a row-partitioned solve: Gp = (all-reduced A'z) + pp with pp = P p + R_x p, and
+// alpha = z'r / p'Gp with p'Gp = the scalar that was all-reduced together with the shared block (Gs[-1]);
+// z'r counts the columns >= cnt_lo
+__global__ void __launch_bounds__(kThreads)
+k_cg_update_dist(double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, const double *__restrict__ p,
+                 const double *__restrict__ Gs, const double *__restrict__ pp, const double *__restrict__ M, int n,
+                 int cnt_lo, RedWs ws, DevScalars *S, CgCtl ctl) {
+  if (S->cg_done) return;
+  const double alpha = S->ztr / Gs[-1];
+  double v[2] = {0.0, 0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    x[j] = fma(alpha, p[j], x[j]);
+    const double rj = fma(-alpha, Gs[j] + pp[j], r[j]);
+    const double zj = rj * M[j];
+    r[j] = rj;
+    z[j] = zj;
+    if (j >= cnt_lo) v[0] = fma(zj, rj, v[0]);
+    v[1] = fmax(v[1], fabs(rj));
+  }
+  grid_reduce_fin<1, 1>(v, ws, S, FinCgUpdate{ctl});
+}
+// r = b - (Gs + pp) ; x = s ; z = M r ; p = z   (warm-started CG start of a row-partitioned solve)
+__global__ void __launch_bounds__(kThreads)
+k_cg_start_dist(double *__restrict__ b, const double *__restrict__ s, const double *__restrict__ Gs,
+                const double *__restrict__ pp, const double *__restrict__ M, double *__restrict__ r,
+                double *__restrict__ z, double *__restrict__ p, int n, int cnt_lo, RedWs ws, DevScalars *S, CgCtl ctl) {
+  if (S->cg_done) return;
+  double v[2] = {0.0, 0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const double rj = b[j] - (Gs[j] + pp[j]);
+    const double zj = rj * M[j];
+    b[j] = s[j];
+    r[j] = rj;
+    z[j] = zj;
+    p[j] = zj;
+    if (j >= cnt_lo) v[0] = fma(zj, rj, v[0]);
+    v[1] = fmax(v[1], fabs(rj));
+  }
+  grid_reduce_fin<1, 1>(v, ws, S, FinCgStart{ctl});
 }
 
 // p = z + beta p                                         (private.c:213-216)
@@ -273,7 +387,9 @@ int LinSys::init(Ctx *ctx, const ScsMatrix *Ah, const ScsMatrix *Ph) {
   if (dev_alloc(&Pdiag, (size_t)n) || h2d(*c, Pdiag, pd.data(), (size_t)n)) return -1;
   if (c->sync()) return -1;
   if (chunks_build(*c, chA, A, nullptr)) return -1;
-  if (chunks_build(*c, chAt, At, hasP ? &P : nullptr)) return -1;
+  // row-partitioned mode: A_g' z_g is all-reduced before P p + R_x p is added, so the two row sets get
+  // their own chunk lists (and their own launches)
+  if (chunks_build(*c, chAt, At, (hasP && !c->dist) ? &P : nullptr)) return -1;
   if (c->dist && chunks_build(*c, chP, P, nullptr)) return -1;
   {
     const long long mi = 10ll * n;  // private.c:299
@@ -281,10 +397,14 @@ int LinSys::init(Ctx *ctx, const ScsMatrix *Ah, const ScsMatrix *Ph) {
     CUDA_OK(cudaMemcpyAsync(&c->S->cg_max_its, &mi32, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
   }
+  // Gp carries kGpFront doubles in front of it: Gp[-1] is the scalar p'Gp of a row-partitioned solve,
+  // all-reduced in one call with the shared block Gp[0, n_sh) (Gp[-2] pads the region to 16 bytes)
   if (dev_alloc_zero(&M, (size_t)n, c->stream) || dev_alloc_zero(&p, (size_t)n, c->stream) ||
-      dev_alloc_zero(&r, (size_t)n, c->stream) || dev_alloc_zero(&Gp, (size_t)n, c->stream) ||
+      dev_alloc_zero(&r, (size_t)n, c->stream) || dev_alloc_zero(&Gp_base, (size_t)n + kGpFront, c->stream) ||
       dev_alloc_zero(&z, (size_t)n, c->stream) || dev_alloc_zero(&tmp, (size_t)m, c->stream))
     return -1;
+  Gp = Gp_base + kGpFront;
+  if (c->dist && dev_alloc_zero(&pp, (size_t)n, c->stream)) return -1;
   return 0;
 }
 
@@ -292,10 +412,11 @@ int LinSys::finalize_structure() {
   tA.destroy();
   tG.destroy();
   const int mode = tiled_env_mode();  // SCS_B200_TILED: 0 never, 1 force, unset: heuristic
-  if (mode == 0 || c->dist) return 0;
+  if (mode == 0) return 0;
   if (tiled_prepare()) return -1;
   if (tA.build(*c, A, nullptr, mode == 1)) return -1;
-  if (tG.build(*c, At, hasP ? &P : nullptr, mode == 1)) return -1;
+  // row-partitioned mode: A_g' alone (P p + R_x p is a separate pass after the all-reduce)
+  if (tG.build(*c, At, (hasP && !c->dist) ? &P : nullptr, mode == 1)) return -1;
   return 0;
 }
 
@@ -313,7 +434,8 @@ void LinSys::destroy() {
   if (own_diag_r) dev_free(diag_r);
   diag_r = nullptr;
   dev_free(Pdiag);
-  dev_free(M); dev_free(p); dev_free(r); dev_free(Gp); dev_free(z); dev_free(tmp);
+  dev_free(M); dev_free(p); dev_free(r); dev_free(Gp_base); dev_free(z); dev_free(tmp); dev_free(pp);
+  Gp = nullptr;
 }
 
 // Refresh P's diagonal from the (possibly re-scaled) device copy of P.
@@ -336,7 +458,7 @@ int LinSys::update_precond() {
     EpiStore es; es.y = M;
     row_kernel<ElemSqDiv, ElemSqDiv, EpiStore, false>
         <<<chAt.grid, kThreads, 0, c->stream>>>(At, e, At, e, chAt.d, chAt.n, es, c->red, c->S, nullptr);
-    if (dist_allreduce(*c, M, (size_t)n, 0)) return -1;
+    if (dist_allreduce(*c, M, (size_t)c->n_sh, 0)) return -1;  // private columns are complete locally
     k_precond_fin<<<ew_grid(*c, n), kThreads, 0, c->stream>>>(M, diag_r, Pdiag, n);
     c->launches += 2;
     CUDA_OK(cudaGetLastError());
@@ -349,6 +471,34 @@ int LinSys::update_precond() {
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+// row-partitioned CG: the same product with the m-space part of p'Gp reduced on the side (EpiScaleRyDot)
+int LinSys::launch_A_scaled_dot(const double *x, double *out, const int *skip) {
+  EpiScaleRyDot epi;
+  epi.out = out; epi.ry = diag_r + n; epi.S_ = c->S;
+  ElemMul e{x};
+  if (tA.ok && tiled_aligned(x))
+    tiled_launch(tA, x, nullptr, epi, *c, skip, 0);
+  else
+    row_kernel<ElemMul, ElemMul, EpiScaleRyDot, false>
+        <<<chA.grid, kThreads, 0, c->stream>>>(A, e, A, e, chA.d, chA.n, epi, c->red, c->S, skip);
+  return 0;
+}
+
+// row-partitioned mode: out[0, n) = A_g' zin of the local rows, shared block [0, n_sh) summed over the
+// ranks in place.  with_scalar: out[-1] (this rank's contribution to a scalar, written beforehand) rides along.
+int LinSys::dist_At(const double *zin, double *out, const int *skip, bool with_scalar, int kt_cat) {
+  EpiStoreT es;
+  es.y = out; es.S_ = c->S; es.kt_cat = kt_cat;
+  ElemMul ea{zin};
+  if (tG.ok && tiled_aligned(zin))
+    tiled_launch(tG, zin, nullptr, es, *c, skip, kt_cat);
+  else
+    row_kernel<ElemMul, ElemMul, EpiStoreT, false>
+        <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, At, ea, chAt.d, chAt.n, es, c->red, c->S, skip);
+  if (with_scalar) return dist_allreduce(*c, out - 2, (size_t)c->n_sh + 2, 0);
+  return dist_allreduce(*c, out, (size_t)c->n_sh, 0);
 }
 
 int LinSys::launch_A_scaled(const double *x, double *out, const int *skip, int tag, bool counted) {
@@ -372,14 +522,13 @@ int LinSys::launch_G(const double *zin, const double *pin, double *out, const in
   ElemMul ea{zin}, eb{pin};
   (void)tag;
   if (c->dist) {
-    // out = A_g' z_g (local rows), summed over the ranks; then P p + R_x p and p'Gp on every rank
-    EpiStore es; es.y = out;
-    row_kernel<ElemMul, ElemMul, EpiStore, false>
-        <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, At, ea, chAt.d, chAt.n, es, c->red, c->S, skip);
-    if (dist_allreduce(*c, out, (size_t)n, 0)) return -1;
-    epi.extra = out;
-    row_kernel<ElemMul, ElemMul, EpiG, false>
-        <<<chP.grid, kThreads, 0, c->stream>>>(P, eb, P, eb, chP.d, chP.n, epi, c->red, c->S, skip);
+    // pp = P p + R_x p and this rank's contribution to p'Gp -> out[-1]; out = A_g' z_g of the local rows;
+    // ONE all-reduce of [out[-1] | shared block of out].  The consumers (k_cg_update_dist) add pp.
+    EpiPP ep;
+    ep.pp = pp; ep.p = pin; ep.rx = diag_r; ep.slot = out - 1; ep.cnt_lo = c->cnt_lo;
+    row_kernel<ElemMul, ElemMul, EpiPP, false>
+        <<<chP.grid, kThreads, 0, c->stream>>>(P, eb, P, eb, chP.d, chP.n, ep, c->red, c->S, skip);
+    if (dist_At(zin, out, skip, true, 1)) return -1;
     if (counted) { c->launches += 2; c->spmv_calls += 2; }
     return 0;
   }
@@ -412,12 +561,8 @@ int LinSys::enqueue_head(double *b, const double *ws, CgCtl ctl) {
   // tmp = R_y^-1 ry ; b[:n] += A' tmp
   k_scale_ry<<<gm, kThreads, 0, st>>>(b + n, diag_r + n, tmp, m, done);
   if (cx.dist) {
-    EpiStore es; es.y = z;  // z is free until CG starts
-    ElemMul e{tmp};
-    row_kernel<ElemMul, ElemMul, EpiStore, false>
-        <<<chAt.grid, kThreads, 0, st>>>(At, e, At, e, chAt.d, chAt.n, es, cx.red, S, done);
-    if (dist_allreduce(cx, z, (size_t)n, 0)) return -1;
-    k_add_if<<<gn, kThreads, 0, st>>>(b, z, n, done);
+    if (dist_At(tmp, Gp, done, false, -1)) return -1;  // Gp is free until the CG iterations start
+    k_add_if<<<gn, kThreads, 0, st>>>(b, Gp, n, done);
     cx.launches++;
   } else {
     EpiRhs epi; epi.b = b;
@@ -433,14 +578,15 @@ int LinSys::enqueue_head(double *b, const double *ws, CgCtl ctl) {
     epi.extra = nullptr;
     ElemMul ea{tmp}, eb{ws};
     if (cx.dist) {
-      EpiStore es; es.y = r;
-      row_kernel<ElemMul, ElemMul, EpiStore, false>
-          <<<chAt.grid, kThreads, 0, st>>>(At, ea, At, ea, chAt.d, chAt.n, es, cx.red, S, done);
-      if (dist_allreduce(cx, r, (size_t)n, 0)) return -1;
-      epi.extra = r;
-      row_kernel<ElemMul, ElemMul, EpiG0, false>
-          <<<chP.grid, kThreads, 0, st>>>(P, eb, P, eb, chP.d, chP.n, epi, cx.red, S, done);
-      cx.launches++;
+      // r = b - (A' R_y^-1 A s + P s + R_x s): A_g' (tmp) all-reduced into Gp, pp = P s + R_x s
+      EpiPP ep;
+      ep.pp = pp; ep.p = ws; ep.rx = diag_r; ep.slot = Gp - 1; ep.cnt_lo = cx.cnt_lo;
+      row_kernel<ElemMul, ElemMul, EpiPP, false>
+          <<<chP.grid, kThreads, 0, st>>>(P, eb, P, eb, chP.d, chP.n, ep, cx.red, S, done);
+      if (dist_At(tmp, Gp, done, false, -1)) return -1;
+      k_cg_start_dist<<<gn, kThreads, 0, st>>>(b, ws, Gp, pp, M, r, z, p, n, cx.cnt_lo, cx.red, S, ctl);
+      if (dist_finish(cx, 1, 1, FinCgStart{ctl})) return -1;
+      cx.launches += 2;
     } else if (tG.ok && tiled_aligned(tmp) && tiled_aligned(ws))
       cx.launches += tiled_launch(tG, tmp, ws, epi, cx, done) - 1;
     else if (hasP)
@@ -451,7 +597,8 @@ int LinSys::enqueue_head(double *b, const double *ws, CgCtl ctl) {
           <<<chAt.grid, kThreads, 0, st>>>(At, ea, P, eb, chAt.d, chAt.n, epi, cx.red, S, done);
     cx.launches++; cx.spmv_calls++;
   } else {
-    k_cg_init_cold<<<gn, kThreads, 0, st>>>(b, M, r, z, p, n, cx.red, S, ctl);
+    k_cg_init_cold<<<gn, kThreads, 0, st>>>(b, M, r, z, p, n, cx.cnt_lo, cx.red, S, ctl);
+    if (dist_finish(cx, 1, 1, FinCgStart{ctl})) return -1;
     cx.launches++;
   }
   return 0;
@@ -464,6 +611,15 @@ int LinSys::enqueue_cg_iter(double *b, CgCtl ctl, int tag) {
   const int gn = ew_grid(cx, n);
   // not added to cx.launches: the number of CG iterations that really execute is decided on
   // the device (S->cg_its_total); launch totals are 4 * that counter + cx.launches
+  if (cx.dist) {
+    launch_A_scaled_dot(p, tmp, done);
+    if (launch_G(tmp, p, Gp, done, tag, false)) return -1;
+    k_cg_update_dist<<<gn, kThreads, 0, cx.stream>>>(b, r, z, p, Gp, pp, M, n, cx.cnt_lo, cx.red, S, ctl);
+    if (dist_finish(cx, 1, 1, FinCgUpdate{ctl})) return -1;
+    cx.launches--;  // (dist_finish counted its finaliser; the CG-loop kernels are counted per executed iteration)
+    k_cg_pupdate<<<gn, kThreads, 0, cx.stream>>>(p, z, n, S);
+    return 0;
+  }
   launch_A_scaled(p, tmp, done, tag, false);
   launch_G(tmp, p, Gp, done, tag, false);
   k_cg_update<<<gn, kThreads, 0, cx.stream>>>(b, r, z, p, Gp, M, n, cx.red, S, ctl);
@@ -495,6 +651,9 @@ int LinSys::solve_dev_loop(double *b, int first_batch) {
   const long long max_its = 10ll * n;  // private.c:299
   int batch = first_batch > 0 ? first_batch : (last_its + 1 < 1 ? 1 : last_its + 1);
   if (batch > 64) batch = 64;
+  // row-partitioned mode: an iteration enqueued after convergence still pays its collectives (NCCL kernels
+  // do not read the stop flag), so the first batch undershoots by one and the top-ups are small
+  if (cx.dist && first_batch <= 0) batch = last_its > 2 ? last_its - 1 : 1;
   long long enq = 0;
   int its = 0;
   for (;;) {
@@ -502,7 +661,7 @@ int LinSys::solve_dev_loop(double *b, int first_batch) {
     if (cx.fetch_scalars()) return -1;
     its = cx.S_host->cg_its;
     if (cx.S_host->cg_done || enq >= max_its) break;
-    batch = batch < 32 ? batch * 2 : 64;
+    batch = cx.dist ? 2 : (batch < 32 ? batch * 2 : 64);
   }
   if (first_batch <= 0) last_its = its;
   tot_cg_its += its;

@@ -27,10 +27,9 @@ struct LinSys {
   CsrDev A, At, P;  // CSR(A): m rows; CSR(A'): n rows; full symmetric CSR(P): n rows
   bool hasP = false;
   ChunkList chA, chAt;   // chAt is built over the fused (A', P) rows
-  // row-partitioned mode: chunk list over the n rows of P alone.  P is replicated, so this
-  // list -- and with it the summation order of every reduction over replicated n-space data
-  // (p'Gp, z'r, x'Px ...) -- is identical on all ranks, which keeps the CG scalars and hence
-  // the ranks' control flow bit-identical.
+  // row-partitioned mode: chunk list over the n rows of P alone (P p + R_x p is added after the
+  // all-reduce of A_g' z_g).  Every data-dependent scalar is produced by dist_finish from the ranks' raw
+  // values in rank order, so the CG scalars and hence the ranks' control flow are bit-identical.
   ChunkList chP;
   // tiled shared-memory format (tiled.cuh) of CSR(A) and of [CSR(A') | CSR(P)], built by
   // finalize_structure() for large matrices; the CG-loop products go through it when present
@@ -39,6 +38,9 @@ struct LinSys {
   bool own_diag_r = false;
   double *Pdiag = nullptr;  // n (zeros when !hasP)
   double *M = nullptr, *p = nullptr, *r = nullptr, *Gp = nullptr, *z = nullptr;  // n
+  static constexpr int kGpFront = 8;  // doubles allocated in front of Gp (Gp[-1]: all-reduced scalar, dist mode)
+  double *Gp_base = nullptr;
+  double *pp = nullptr;  // n, row-partitioned mode only: P p + R_x p
   double *tmp = nullptr;                                                          // m
   long long tot_cg_its = 0;
   int last_its = 2;
@@ -67,8 +69,11 @@ struct LinSys {
   // kernels of one CG iteration (enqueue_cg_iter): two products + two vector updates; a tiled product is
   // two launches (streaming kernel, epilogue pass)
   static int tiled_launches(const TiledOp &t) { return t.ok ? (t.has_tiled ? 2 : 1) : 1; }
-  int cg_iter_launches() const { return 2 + tiled_launches(tA) + tiled_launches(tG); }
+  int cg_iter_launches() const { return (c && c->dist ? 4 : 2) + tiled_launches(tA) + tiled_launches(tG); }
   double bytes_P() const { return hasP ? 12.0 * P.nnz + 4.0 * (n + 1) + 16.0 * n : 0.0; }
+  // row-partitioned mode (dist.cuh)
+  int launch_A_scaled_dot(const double *x, double *out, const int *skip);
+  int dist_At(const double *zin, double *out, const int *skip, bool with_scalar, int kt_cat);
   // launchers shared with the ADMM driver
   int launch_A_scaled(const double *x, double *out, const int *skip, int tag = -1, bool counted = true);  // out = R_y^-1 A x
   int launch_G(const double *zin, const double *pin, double *out, const int *skip, int tag = -1,

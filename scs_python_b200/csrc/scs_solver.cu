@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <chrono>
 #include <csignal>
+#include <mutex>
 #include <string>
 
 #include "aa.cuh"
@@ -51,11 +52,17 @@ static inline int ew_grid(const Ctx &c, long long len) {
 }
 
 // ------------------------------------------------------------ SIGINT (ctrlc.c) --------
+// The handler flag is the only process-wide state (as in the reference, whose ctrlc.c guards it with a
+// mutex).  Workspaces solve concurrently from different threads (scsobject.h:984-987 releases the GIL), so
+// installing / restoring the handler is reference-counted under a mutex, and the flag is only cleared by
+// the solve that installs the handler -- never while another solve is listening.
 static volatile sig_atomic_t g_int_detected = 0;
 static struct sigaction g_old_action;
 static int g_listener_depth = 0;
+static std::mutex g_listener_mu;
 static void b200_sigint_handler(int) { g_int_detected = 1; }
 static void start_interrupt_listener() {
+  std::lock_guard<std::mutex> lk(g_listener_mu);
   if (g_listener_depth++ == 0) {
     struct sigaction act;
     g_int_detected = 0;
@@ -66,6 +73,7 @@ static void start_interrupt_listener() {
   }
 }
 static void end_interrupt_listener() {
+  std::lock_guard<std::mutex> lk(g_listener_mu);
   if (g_listener_depth > 0 && --g_listener_depth == 0) {
     struct sigaction act;
     sigaction(SIGINT, &g_old_action, &act);
@@ -267,10 +275,11 @@ struct FinRootPlus {  // the quadratic of scs.c:676-687
 // root_plus (scs.c:667-688): p = u_t (after the solve), mu = v, eta = v[l-1]
 __global__ void __launch_bounds__(kThreads)
 k_rootplus(const double *__restrict__ u_t, const double *__restrict__ v, const double *__restrict__ g,
-           const double *__restrict__ R, int n, int nm, int own_x, RedWs red, DevScalars *S) {
+           const double *__restrict__ R, int n, int nm, int cnt_lo, RedWs red, DevScalars *S) {
   double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  // own_x == 0: rank > 0 of a row-partitioned solve, the replicated x block is summed by rank 0
-  for (int j = (own_x ? 0 : n) + blockIdx.x * blockDim.x + threadIdx.x; j < nm; j += gridDim.x * blockDim.x) {
+  // cnt_lo > 0: rank > 0 of a row-partitioned solve, the replicated shared block [0, cnt_lo) is summed by rank 0
+  (void)n;
+  for (int j = cnt_lo + blockIdx.x * blockDim.x + threadIdx.x; j < nm; j += gridDim.x * blockDim.x) {
     const double ri = R[j], gi = g[j], pi = u_t[j], mui = v[j];
     s[0] = fma(gi * gi, ri, s[0]);
     s[1] = fma(mui * gi, ri, s[1]);
@@ -322,7 +331,8 @@ struct FinPost {
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_post(double *__restrict__ v, double *__restrict__ rsk, const double *__restrict__ u, const double *__restrict__ u_t,
-       const double *__restrict__ R, int n, int l, int own_x, double alpha, RedWs red, DevScalars *S) {
+       const double *__restrict__ R, int n, int l, int cnt_lo, double alpha, RedWs red, DevScalars *S) {
+  (void)n;
   if (MODE != 2 && blockIdx.x == 0 && threadIdx.x == 0) phase_lap(S, 1);  // cone interval ends
   double s[1] = {0.0};
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < l; j += gridDim.x * blockDim.x) {
@@ -331,8 +341,8 @@ k_post(double *__restrict__ v, double *__restrict__ rsk, const double *__restric
     if (MODE != 1) {
       const double vn = fma(alpha, uj - utj, vj);
       v[j] = vn;
-      // own_x == 0: the replicated x block and tau are summed by rank 0 only
-      if (own_x || (j >= n && j < l - 1)) s[0] = fma(vn, vn, s[0]);
+      // cnt_lo > 0: the replicated shared block [0, cnt_lo) and tau are summed by rank 0 only
+      if (cnt_lo == 0 || (j >= cnt_lo && j < l - 1)) s[0] = fma(vn, vn, s[0]);
     }
   }
   if (MODE != 1) grid_reduce_fin<1, 0>(s, red, S, FinPost{});
@@ -399,6 +409,19 @@ struct EpiResA {
     grid_reduce_fin<1, 7>(v, ws, S, FinResA{u + n + m_, rsk + n + m_});
   }
 };
+struct FinResAt {
+  __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    S->res[R_XPX_TAU] = o[0];
+    S->res[R_CTX_TAU] = o[1];
+    S->res[R_NM_PX_ATY_CTAU] = o[2];
+    S->res[R_NM_PX] = o[3];
+    S->res[R_NM_ATY] = o[4];
+    S->res[R_ONM_PX_ATY_CTAU] = o[5];
+    S->res[R_ONM_PX] = o[6];
+    S->res[R_ONM_ATY] = o[7];
+    S->nm_px_aty_ctau = o[2];
+  }
+};
 // dual pass over (CSR(A'), CSR(P)), gathers y = u[n:] and x = u[0:n]
 struct EpiResAt {
   static constexpr bool kSeparate = true;
@@ -407,6 +430,7 @@ struct EpiResAt {
   int n, m_;
   double inv_ps;
   const double *extra;  // row-partitioned mode: all-reduced A'y (the kernel then runs over P only), else null
+  int cnt_lo = 0;       // row-partitioned mode: the sums count columns >= cnt_lo (shared block on rank 0 only)
   __device__ __forceinline__ void init(State &s) const {
     s.xpx = 0.0; s.ctx = 0.0;
 #pragma unroll
@@ -421,8 +445,10 @@ struct EpiResAt {
     const double xj = u[j], cj = c[j];
     const double pac = px + aty + tau * cj;
     const double f = inv_ps / E[j];
-    st.xpx = fma(px, xj, st.xpx);
-    st.ctx = fma(xj, cj, st.ctx);
+    if (j >= cnt_lo) {
+      st.xpx = fma(px, xj, st.xpx);
+      st.ctx = fma(xj, cj, st.ctx);
+    }
     st.m[0] = fmax(st.m[0], fabs(pac));
     st.m[1] = fmax(st.m[1], fabs(px));
     st.m[2] = fmax(st.m[2], fabs(aty));
@@ -432,17 +458,7 @@ struct EpiResAt {
   }
   __device__ __forceinline__ void finish(State &st, const RedWs &ws, DevScalars *S) const {
     double v[8] = {st.xpx, st.ctx, st.m[0], st.m[1], st.m[2], st.m[3], st.m[4], st.m[5]};
-    grid_reduce<2, 6>(v, ws, [S](double *o) {
-      S->res[R_XPX_TAU] = o[0];
-      S->res[R_CTX_TAU] = o[1];
-      S->res[R_NM_PX_ATY_CTAU] = o[2];
-      S->res[R_NM_PX] = o[3];
-      S->res[R_NM_ATY] = o[4];
-      S->res[R_ONM_PX_ATY_CTAU] = o[5];
-      S->res[R_ONM_PX] = o[6];
-      S->res[R_ONM_ATY] = o[7];
-      S->nm_px_aty_ctau = o[2];
-    });
+    grid_reduce_fin<2, 6>(v, ws, S, FinResAt{});
   }
 };
 
@@ -474,6 +490,11 @@ k_finalize_sol(double *__restrict__ xo, double *__restrict__ yo, double *__restr
     }
   }
   grid_reduce_fin<1, 2>(v, red, S, FinSol{});
+}
+// row-partitioned mode: full[loc2glob[j]] = x[j] for the columns this rank counts
+__global__ void __launch_bounds__(kThreads)
+k_scatter_cols(double *__restrict__ full, const double *__restrict__ x, const int *__restrict__ loc2glob, int lo, int n) {
+  for (int j = lo + blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) full[loc2glob[j]] = x[j];
 }
 __global__ void __launch_bounds__(kThreads)
 k_scale3(double *__restrict__ x, int n, double fx, double *__restrict__ y, double *__restrict__ s, int m, double fy,
@@ -565,9 +586,14 @@ struct SCS_WORK {
   long long graph_launches = 0, graph_spmv = 0;  // fixed (non-CG-loop) kernels per graph launch
   long long n_checks = 0, n_aa = 0;               // residual checks / AA applications so far
   // row-partitioned mode (dist.cuh): this rank owns rows [row0, row0 + m) of the m_total rows
+  // and the columns [shared (n_sh, replicated) | private to this rank] of the n_total columns
   bool dist = false;
-  int rank = 0, world = 1, m_total = 0, row0 = 0, own_x = 1;
-  double *gather = nullptr;  // m_total doubles: assembling the full y / s on every rank
+  bool print_rank0 = false, verbose_collective = false;  // dist mode: who prints / whether the verbose-only residual passes run
+  int rank = 0, world = 1, m_total = 0, row0 = 0, n_total = 0, n_sh = 0;
+  int cnt_lo = 0;  // reductions over n-space count [cnt_lo, n): 0 on rank 0, n_sh elsewhere (shared block counted once)
+  std::vector<int> loc2glob;   // global index of every local column
+  int *d_loc2glob = nullptr;
+  double *gather = nullptr;  // max(m_total, n_total) doubles: assembling the full x / y / s on every rank
   ScsSettings stgs;
   std::string write_fn, csv_fn;
   // device state
@@ -576,7 +602,7 @@ struct SCS_WORK {
   double *sol_x = nullptr, *sol_y = nullptr, *sol_s = nullptr;
   double *csv_m = nullptr, *csv_n = nullptr;  // A x and A'y + P x of the CSV trace (allocated on first use)
   // host
-  std::vector<double> b_orig, c_orig;
+  std::vector<double> b_orig, c_orig, c_loc, x_loc;
   double nm_b_orig = 0, nm_c_orig = 0, primal_scale = 1, dual_scale = 1;
   HostResid r_n, r_o;
   double setup_time = 0;
@@ -801,7 +827,7 @@ static int normalize_a_p_dev(SCS_WORK *w) {
       else
         row_kernel<ElemAbsMax, ElemAbsMax, EpiStoreComb, false>
             <<<ls.chAt.grid, kThreads, 0, st>>>(ls.At, e, ls.P, e, ls.chAt.d, ls.chAt.n, eE, c.red, c.S, nullptr);
-      if (dist_allreduce(c, Et, (size_t)n, 1)) return -1;  // column inf-norms over all ranks' rows
+      if (dist_allreduce(c, Et, (size_t)c.n_sh, 1)) return -1;  // shared columns: inf-norms over all ranks' rows
       k_inv_sqrt_limit<<<ew_grid(c, n), kThreads, 0, st>>>(Et, n, 0);
       c.launches += 4;
     } else {
@@ -811,13 +837,23 @@ static int normalize_a_p_dev(SCS_WORK *w) {
       k_sqrt<<<ew_grid(c, m), kThreads, 0, st>>>(Dt, m);
       if (w->cone.enforce_boundaries(Dt, 1)) return -1;
       k_inv_sqrt_limit<<<ew_grid(c, m), kThreads, 0, st>>>(Dt, m, 0);
-      if (ls.hasP && w->own_x)  // P is replicated: its squares are summed by rank 0 only
+      if (ls.hasP && !c.dist)
         row_kernel<ElemSumSq, ElemSumSq, EpiStoreComb, true>
             <<<ls.chAt.grid, kThreads, 0, st>>>(ls.At, e, ls.P, e, ls.chAt.d, ls.chAt.n, eE, c.red, c.S, nullptr);
       else
         row_kernel<ElemSumSq, ElemSumSq, EpiStoreComb, false>
             <<<ls.chAt.grid, kThreads, 0, st>>>(ls.At, e, ls.P, e, ls.chAt.d, ls.chAt.n, eE, c.red, c.S, nullptr);
-      if (dist_allreduce(c, Et, (size_t)n, 0)) return -1;  // column sums of squares over all ranks' rows
+      if (c.dist) {
+        // shared columns: sums of squares over all ranks' rows; P's rows (replicated on the shared block, local
+        // on the private one) are added afterwards so that they are counted once
+        if (dist_allreduce(c, Et, (size_t)c.n_sh, 0)) return -1;
+        if (ls.hasP) {
+          EpiAccum ea; ea.y = Et;
+          row_kernel<ElemSumSq, ElemSumSq, EpiAccum, false>
+              <<<ls.chP.grid, kThreads, 0, st>>>(ls.P, e, ls.P, e, ls.chP.d, ls.chP.n, ea, c.red, c.S, nullptr);
+          c.launches++;
+        }
+      }
       k_inv_sqrt_limit<<<ew_grid(c, n), kThreads, 0, st>>>(Et, n, 1);
       c.launches += 5;
     }
@@ -874,10 +910,12 @@ static int populate_residuals(SCS_WORK *w, int iter) {
       EpiStore es; es.y = ls.Gp;
       row_kernel<ElemMul, ElemMul, EpiStore, false>
           <<<ls.chAt.grid, kThreads, 0, c.stream>>>(ls.At, ea, ls.At, ea, ls.chAt.d, ls.chAt.n, es, c.red, c.S, nullptr);
-      if (dist_allreduce(c, ls.Gp, (size_t)n, 0)) return -1;
+      if (dist_allreduce(c, ls.Gp, (size_t)c.n_sh, 0)) return -1;
       epi.extra = ls.Gp;
+      epi.cnt_lo = c.cnt_lo;
       row_kernel<ElemMul, ElemMul, EpiResAt, false>
           <<<ls.chP.grid, kThreads, 0, c.stream>>>(ls.P, eb, ls.P, eb, ls.chP.d, ls.chP.n, epi, c.red, c.S, nullptr);
+      if (dist_finish(c, 2, 6, FinResAt{})) return -1;
       c.launches++; c.spmv_calls++;
     } else if (ls.hasP)
       row_kernel<ElemMul, ElemMul, EpiResAt, true>
@@ -1099,7 +1137,7 @@ static void mark_close(SCS_WORK *w, int iter) {
 static int enqueue_front_head(SCS_WORK *w, CgCtl loop) {
   Ctx &c = w->c;
   const int n = w->n, m = w->m, gl = ew_grid(c, w->l);
-  const int l_total = w->dist ? n + w->m_total + 1 : w->l;
+  const int l_total = w->dist ? w->n_total + w->m_total + 1 : w->l;
   cudaStream_t st = c.stream;
   if (w->has_aa)
     k_prep<true><<<gl, kThreads, 0, st>>>(w->v, w->v_prev, w->u_t, w->u, w->g, w->diag_r, w->ws, n, m, l_total, c.red, c.S);
@@ -1114,7 +1152,7 @@ static int enqueue_front_tail(SCS_WORK *w) {
   const int n = w->n, m = w->m, gl = ew_grid(c, w->l);
   cudaStream_t st = c.stream;
   if (w->ls.enqueue_tail(w->u_t)) return -1;
-  k_rootplus<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->u_t, w->v, w->g, w->diag_r, n, n + m, w->own_x, c.red, c.S);
+  k_rootplus<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->u_t, w->v, w->g, w->diag_r, n, n + m, w->cnt_lo, c.red, c.S);
   if (dist_finish(c, 5, 0, FinRootPlus{w->v + n + m, w->diag_r + n + m})) return -1;
   k_pre<<<gl, kThreads, 0, st>>>(w->u_t, w->u, w->rsk, w->v, w->g, w->diag_r, n, m, w->cone.z, w->cone.z + w->cone.l, c.S);
   c.launches += 2;
@@ -1205,7 +1243,7 @@ static void free_work(SCS_WORK *w) {
   if (w->st_body) cudaStreamDestroy(w->st_body);
   dev_free(w->u); dev_free(w->u_t); dev_free(w->v); dev_free(w->v_prev); dev_free(w->rsk); dev_free(w->g);
   dev_free(w->diag_r); dev_free(w->b); dev_free(w->cvec); dev_free(w->D); dev_free(w->E); dev_free(w->ws);
-  dev_free(w->sol_x); dev_free(w->sol_y); dev_free(w->sol_s); dev_free(w->gather);
+  dev_free(w->sol_x); dev_free(w->sol_y); dev_free(w->sol_s); dev_free(w->gather); dev_free(w->d_loc2glob);
   dev_free(w->csv_m); dev_free(w->csv_n);
   w->c.destroy();
   delete w;
@@ -1258,22 +1296,38 @@ static void fill_aa_stats(SCS_WORK *w, ScsInfo *info) {
 // ------------------------------------------------------------- row partition (dist) ---
 // Rank g of a row-partitioned solve owns a contiguous block of rows of A.  Cuts may fall on
 // any row of the zero / nonneg cones and otherwise only between cones, and are
-// placed so that every rank holds about the same number of non-zeros.
+// placed so that every rank holds about the same modelled work (stored entries + a per-row
+// charge for the m-space vector passes).
+//
+// Columns: a column of A whose non-zeros all lie in one rank's rows, and whose row of P holds
+// nothing but the diagonal, is PRIVATE to that rank -- no other rank ever multiplies by it, so its
+// entries of x, c, E, the CG vectors ... exist on that rank only.  Every other column is SHARED
+// (replicated).  The local column order is [shared, ascending | private, ascending]; the shared
+// block is the only part of an n-vector that is ever all-reduced.
 struct LocalProblem {
-  std::vector<double> Ax, b;
-  std::vector<int> Ai, Ap;
-  ScsMatrix A;
+  std::vector<double> Ax, b, c, Px;
+  std::vector<int> Ai, Ap, Pi, Pp;
+  std::vector<int> loc2glob;  // n_loc global column indices
+  ScsMatrix A, P;
   ScsData d;
   ScsCone k;
-  int row0 = 0, m = 0;
+  int row0 = 0, m = 0, n_sh = 0, n_loc = 0;
+  long long nnz_max_rank = 0;
 };
 
-static int partition_rows(const ScsData *d, const ScsCone *k, int rank, int world, LocalProblem &out) {
+static int dist_row_weight() {
+  const char *e = getenv("SCS_B200_DIST_ROW_WEIGHT");
+  return e && *e ? atoi(e) : 4;
+}
+
+// cut[g] .. cut[g+1]: rows of rank g
+static int partition_cuts(const ScsData *d, const ScsCone *k, int world, std::vector<int> &cut) {
   const int m = d->m, n = d->n;
   const ScsMatrix *A = d->A;
-  std::vector<long long> pref((size_t)m + 1, 0);  // non-zeros in rows [0, i)
+  const long long rw = dist_row_weight();
+  std::vector<long long> pref((size_t)m + 1, 0);  // work in rows [0, i)
   for (int t = 0; t < A->p[n]; ++t) pref[(size_t)A->i[t] + 1]++;
-  for (int i = 0; i < m; ++i) pref[(size_t)i + 1] += pref[(size_t)i];
+  for (int i = 0; i < m; ++i) pref[(size_t)i + 1] += pref[(size_t)i] + rw;
   // allowed cut positions beyond the z / l rows: cone boundaries
   std::vector<int> bnd;
   int off = k->z + k->l;
@@ -1289,7 +1343,7 @@ static int partition_rows(const ScsData *d, const ScsCone *k, int rank, int worl
     auto it = std::lower_bound(bnd.begin(), bnd.end(), pos);
     return it == bnd.end() ? m : *it;
   };
-  std::vector<int> cut((size_t)world + 1, 0);
+  cut.assign((size_t)world + 1, 0);
   cut[(size_t)world] = m;
   const long long total = pref[(size_t)m];
   for (int g = 1; g < world; ++g) {
@@ -1304,37 +1358,105 @@ static int partition_rows(const ScsData *d, const ScsCone *k, int rank, int worl
       B200_PRINTF("ERROR: cannot cut %d rows into %d non-empty cone-aligned blocks\n", m, world);
       return -1;
     }
+  return 0;
+}
+
+// owner[j] = rank the column is private to, or -1 when shared
+static void classify_columns(const ScsData *d, const std::vector<int> &cut, int world, std::vector<int> &owner) {
+  const int n = d->n;
+  const ScsMatrix *A = d->A, *P = d->P;
+  owner.assign((size_t)n, 0);
+  auto rank_of = [&](int row) { return (int)(std::upper_bound(cut.begin() + 1, cut.end(), row) - (cut.begin() + 1)); };
+  for (int j = 0; j < n; ++j) {
+    const int s = A->p[j], e = A->p[j + 1];
+    if (e == s) { owner[(size_t)j] = j % world; continue; }  // touched by no row: any rank may own it
+    const int r0 = rank_of(A->i[s]), r1 = rank_of(A->i[e - 1]);  // row indices are sorted inside a column
+    owner[(size_t)j] = (r0 == r1) ? r0 : -1;
+  }
+  if (P)
+    for (int j = 0; j < n; ++j)
+      for (int t = P->p[j]; t < P->p[j + 1]; ++t)
+        if (P->i[t] != j) { owner[(size_t)j] = -1; owner[(size_t)P->i[t]] = -1; }  // coupled columns stay replicated
+  if (const char *e = getenv("SCS_B200_DIST_FORCE_SHARED")) {  // tests: every k-th column is treated as shared
+    const int kk = atoi(e);
+    if (kk > 0)
+      for (int j = 0; j < n; j += kk) owner[(size_t)j] = -1;
+  }
+}
+
+static int partition_rows(const ScsData *d, const ScsCone *k, int rank, int world, LocalProblem &out) {
+  const int n = d->n;
+  const ScsMatrix *A = d->A;
+  std::vector<int> cut, owner;
+  if (partition_cuts(d, k, world, cut)) return -1;
+  classify_columns(d, cut, world, owner);
   const int r0 = cut[(size_t)rank], r1 = cut[(size_t)rank + 1];
   out.row0 = r0;
   out.m = r1 - r0;
-  // local CSC: rows [r0, r1) of every column (row indices are sorted inside a column)
-  out.Ap.assign((size_t)n + 1, 0);
-  for (int j = 0; j < n; ++j) {
+  // local columns: shared first, then this rank's private ones
+  out.loc2glob.clear();
+  for (int j = 0; j < n; ++j) if (owner[(size_t)j] < 0) out.loc2glob.push_back(j);
+  out.n_sh = (int)out.loc2glob.size();
+  for (int j = 0; j < n; ++j) if (owner[(size_t)j] == rank) out.loc2glob.push_back(j);
+  const int nl = out.n_loc = (int)out.loc2glob.size();
+  if (nl == 0) {
+    B200_PRINTF("ERROR: rank %d of %d would own no column\n", rank, world);
+    return -1;
+  }
+  // local CSC: rows [r0, r1) of every local column (row indices are sorted inside a column)
+  out.Ap.assign((size_t)nl + 1, 0);
+  for (int jl = 0; jl < nl; ++jl) {
+    const int j = out.loc2glob[(size_t)jl];
     const int *b0 = A->i + A->p[j], *b1 = A->i + A->p[j + 1];
     const int *lo = std::lower_bound(b0, b1, r0), *hi = std::lower_bound(b0, b1, r1);
-    out.Ap[(size_t)j + 1] = out.Ap[(size_t)j] + (int)(hi - lo);
+    out.Ap[(size_t)jl + 1] = out.Ap[(size_t)jl] + (int)(hi - lo);
   }
-  out.Ai.resize((size_t)out.Ap[(size_t)n]);
-  out.Ax.resize((size_t)out.Ap[(size_t)n]);
-  for (int j = 0; j < n; ++j) {
+  out.Ai.resize((size_t)out.Ap[(size_t)nl]);
+  out.Ax.resize((size_t)out.Ap[(size_t)nl]);
+  for (int jl = 0; jl < nl; ++jl) {
+    const int j = out.loc2glob[(size_t)jl];
     const int *b0 = A->i + A->p[j], *b1 = A->i + A->p[j + 1];
-    const int lo = (int)(std::lower_bound(b0, b1, r0) - A->i), cnt = out.Ap[(size_t)j + 1] - out.Ap[(size_t)j];
+    const int lo = (int)(std::lower_bound(b0, b1, r0) - A->i), cnt = out.Ap[(size_t)jl + 1] - out.Ap[(size_t)jl];
     for (int t = 0; t < cnt; ++t) {
-      out.Ai[(size_t)out.Ap[(size_t)j] + t] = A->i[lo + t] - r0;
-      out.Ax[(size_t)out.Ap[(size_t)j] + t] = A->x[lo + t];
+      out.Ai[(size_t)out.Ap[(size_t)jl] + t] = A->i[lo + t] - r0;
+      out.Ax[(size_t)out.Ap[(size_t)jl] + t] = A->x[lo + t];
     }
   }
   out.b.assign(d->b + r0, d->b + r1);
-  out.A.x = out.Ax.data(); out.A.i = out.Ai.data(); out.A.p = out.Ap.data(); out.A.m = out.m; out.A.n = n;
+  out.c.resize((size_t)nl);
+  for (int jl = 0; jl < nl; ++jl) out.c[(size_t)jl] = d->c[out.loc2glob[(size_t)jl]];
+  out.A.x = out.Ax.data(); out.A.i = out.Ai.data(); out.A.p = out.Ap.data(); out.A.m = out.m; out.A.n = nl;
   out.d = *d;
-  out.d.m = out.m; out.d.A = &out.A; out.d.b = out.b.data();
+  out.d.m = out.m; out.d.n = nl; out.d.A = &out.A; out.d.b = out.b.data(); out.d.c = out.c.data();
+  out.d.P = nullptr;
+  if (d->P) {  // P restricted to the local columns: a coupled (off-diagonal) pair is shared on both ends, and
+               // the shared block keeps the global order, so the result is still upper triangular and sorted
+    const ScsMatrix *P = d->P;
+    std::vector<int> g2l((size_t)n, -1);
+    for (int jl = 0; jl < nl; ++jl) g2l[(size_t)out.loc2glob[(size_t)jl]] = jl;
+    out.Pp.assign((size_t)nl + 1, 0);
+    for (int jl = 0; jl < nl; ++jl) {
+      const int j = out.loc2glob[(size_t)jl];
+      for (int t = P->p[j]; t < P->p[j + 1]; ++t) {
+        const int il = g2l[(size_t)P->i[t]];
+        if (il < 0) { B200_PRINTF("ERROR: internal: P couples a local column to a foreign private column\n"); return -1; }
+        out.Pi.push_back(il);
+        out.Px.push_back(P->x[t]);
+      }
+      out.Pp[(size_t)jl + 1] = (int)out.Pi.size();
+    }
+    if (out.Pi.empty()) { out.Pi.push_back(0); out.Px.push_back(0.0); }  // keep the pointers non-null
+    out.P.x = out.Px.data(); out.P.i = out.Pi.data(); out.P.p = out.Pp.data(); out.P.m = nl; out.P.n = nl;
+    out.d.P = &out.P;
+  }
   // the cones inside [r0, r1)
   ScsCone &lk = out.k;
   lk = *k;
+  const int zl = k->z + k->l;
   auto overlap = [&](int a0, int a1) { const int lo = a0 > r0 ? a0 : r0, hi = a1 < r1 ? a1 : r1; return hi > lo ? hi - lo : 0; };
   lk.z = overlap(0, k->z);
   lk.l = overlap(k->z, zl);
-  off = zl;
+  int off = zl;
   auto inside = [&](int start) { return start >= r0 && start < r1; };
   if (k->bsize > 0) {
     if (!inside(off)) { lk.bsize = 0; lk.bu = nullptr; lk.bl = nullptr; }
@@ -1406,13 +1528,20 @@ extern "C" scs_int scs_update(ScsWork *w, scs_float *b, scs_float *c) {  // scs.
     for (int i = 0; i < mt; ++i) nm = fmax(nm, fabs(b[i]));
     w->nm_b_orig = nm;
   }
+  const int nt = w->dist ? w->n_total : n;  // c is always the caller's full-length vector
   if (c) {
-    if (w->c_orig.data() != c) memcpy(w->c_orig.data(), c, sizeof(double) * n);
+    if (w->c_orig.data() != c) memcpy(w->c_orig.data(), c, sizeof(double) * nt);
     double nm = 0.0;
-    for (int i = 0; i < n; ++i) nm = fmax(nm, fabs(c[i]));
+    for (int i = 0; i < nt; ++i) nm = fmax(nm, fabs(c[i]));
     w->nm_c_orig = nm;
   }
-  if (h2d(cx, w->b, w->b_orig.data() + w->row0, (size_t)m) || h2d(cx, w->cvec, w->c_orig.data(), (size_t)n)) return -1;
+  if (w->dist) {  // this rank's columns of c
+    w->c_loc.resize((size_t)n);
+    for (int j = 0; j < n; ++j) w->c_loc[(size_t)j] = w->c_orig[(size_t)w->loc2glob[(size_t)j]];
+  }
+  if (h2d(cx, w->b, w->b_orig.data() + w->row0, (size_t)m) ||
+      h2d(cx, w->cvec, w->dist ? w->c_loc.data() : w->c_orig.data(), (size_t)n))
+    return -1;
   if (w->stgs.normalize) {  // SCS(normalize_b_c), normalize.c:33-61
     k_scale_bc<<<ew_grid(cx, n + m), kThreads, 0, cx.stream>>>(w->b, w->D, m, w->cvec, w->E, n, cx.red, cx.S);
     if (dist_finish(cx, 0, 2, FinSigma{})) return -1;
@@ -1443,20 +1572,22 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
   const ScsCone *k_full = k;
   LocalProblem local;
   Dist *dd = dist_current();
-  if (dd->on()) {  // keep rows [row0, row0 + m) of A, b and the cones inside them
+  if (dd->on() || dd->selftest) {  // keep rows [row0, row0 + m) of A, b, the cones inside them and the columns they touch
+    if (dd->world > kMaxWorld) { B200_PRINTF("ERROR: at most %d ranks\n", kMaxWorld); delete w; return nullptr; }
     if (partition_rows(d, k, dd->rank, dd->world, local)) { delete w; return nullptr; }
-    w->dist = true; w->rank = dd->rank; w->world = dd->world; w->own_x = dd->rank == 0;
-    w->m_total = d->m; w->row0 = local.row0;
+    w->dist = true; w->rank = dd->rank; w->world = dd->world;
+    w->m_total = d->m; w->row0 = local.row0; w->n_total = d->n; w->n_sh = local.n_sh;
+    w->cnt_lo = dd->rank == 0 ? 0 : local.n_sh;
+    w->loc2glob = local.loc2glob;
     d = &local.d;
     k = &local.k;
-    if (dd->rank != 0) w->stgs.verbose = 0;
-    if (w->stgs.acceleration_lookback != 0) {
-      if (w->stgs.verbose) B200_PRINTF("NOTE: Anderson acceleration is switched off in the row-partitioned mode.\n");
-      w->stgs.acceleration_lookback = 0;
-    }
+    // every rank walks the same sequence of collectives: what rank 0 prints is decided by print_rank0 only
+    w->print_rank0 = w->stgs.verbose && dd->rank == 0;
+    w->verbose_collective = w->stgs.verbose != 0;
+    w->stgs.verbose = 0;
     w->stgs.time_limit_secs = 0.;  // host clocks differ between ranks; the loop must stay collective
   }
-  if (w->stgs.verbose) print_init_header(d_full, k_full, &w->stgs);
+  if (w->stgs.verbose || w->print_rank0) print_init_header(d_full, k_full, &w->stgs);
   w->n = d->n; w->m = d->m; w->l = d->n + d->m + 1;
   const int n = w->n, m = w->m, l = w->l;
   if (stgs->write_data_filename) {  // scs.c:1219-1222 (the full problem, before any partitioning)
@@ -1476,10 +1607,12 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
     Ctx &c = w->c;
     cudaStream_t st = c.stream;
     if (w->dist) {
-      c.dist = true;
-      const int one = 1;
-      if (cudaMemcpyAsync(&c.S->dist, &one, sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) break;
-      if (dev_alloc_zero(&w->gather, (size_t)w->m_total, st)) break;
+      c.dist = true; c.rank = w->rank; c.world = w->world; c.n_sh = w->n_sh; c.cnt_lo = w->cnt_lo;
+      const int hdr[3] = {1, w->rank, w->world};  // DevScalars::dist, dist_rank, dist_world
+      if (cudaMemcpyAsync(&c.S->dist, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+      const int glen = w->m_total > w->n_total ? w->m_total : w->n_total;
+      if (dev_alloc_zero(&w->gather, (size_t)glen, st)) break;
+      if (dev_alloc(&w->d_loc2glob, w->loc2glob.size()) || h2d(c, w->d_loc2glob, w->loc2glob.data(), w->loc2glob.size())) break;
     }
     if (dev_alloc_zero(&w->u, (size_t)l, st) || dev_alloc_zero(&w->u_t, (size_t)l, st) ||
         dev_alloc_zero(&w->v, (size_t)l, st) || dev_alloc_zero(&w->v_prev, (size_t)l, st) ||
@@ -1492,7 +1625,7 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
       break;
     }
     w->b_orig.assign((size_t)(w->dist ? w->m_total : m), 0.0);
-    w->c_orig.assign((size_t)n, 0.0);
+    w->c_orig.assign((size_t)(w->dist ? w->n_total : n), 0.0);
     if (w->cone.init(&w->c, k, m)) { B200_PRINTF("ERROR: init_cone failure\n"); break; }
     if (set_diag_r(w)) break;
     if (w->ls.init(&w->c, d->A, d->P)) { B200_PRINTF("ERROR: init_lin_sys_work failure\n"); break; }
@@ -1513,13 +1646,15 @@ extern "C" ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettin
       if (w->cone.normalize_box(Dh.empty() ? nullptr : Dh.data())) break;
     }
     if (w->ls.finalize_structure()) { B200_PRINTF("ERROR: tiled SpMV format failure\n"); break; }
-    if (scs_update(w, d_full->b, d->c)) break;
+    if (scs_update(w, d_full->b, d_full->c)) break;
     if (w->ls.update_precond()) break;
     if (w->stgs.acceleration_lookback) {
       if (w->aa.init(&w->c, l, w->stgs.acceleration_lookback, w->stgs.acceleration_lookback,
                      w->stgs.acceleration_type_1, w->stgs.acceleration_regularization,
                      w->stgs.acceleration_relaxation, kAaSafeguard, kAaMaxWeight, kAaIrSteps) == 0) {
         w->has_aa = w->aa.mem > 0;
+        // row-partitioned mode: the shared block of x and tau are replicated; rank 0 counts them
+        if (w->dist && w->has_aa && w->aa.set_counted_rows(w->cnt_lo, w->rank == 0 ? l : l - 1)) break;
       } else {
         // the reference continues without acceleration when aa_init fails (scs.c:1056-1058)
         if (w->stgs.verbose) B200_PRINTF("WARN: aa_init returned NULL, no acceleration applied.\n");
@@ -1553,6 +1688,7 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   cudaStream_t st = c.stream;
   const int n = w->n, m = w->m, l = w->l;
   const int m_out = w->dist ? w->m_total : m;  // length of the caller's y and s
+  const int n_out = w->dist ? w->n_total : n;  // ... and x
   ScsSettings *stgs = &w->stgs;
   stgs->warm_start = warm_start;
   start_interrupt_listener();
@@ -1566,19 +1702,28 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   cudaMemsetAsync(&c.S->aa_rejected, 0, 2 * sizeof(int), st);  // safeguard counters of this solve
   if (warm_start) {
     if (!sol->x || !sol->y || !sol->s) {
-      return failure(w, m_out, n, sol, info, SCS_FAILED, "warm-start requested without x, y, s", "failure");
+      return failure(w, m_out, n_out, sol, info, SCS_FAILED, "warm-start requested without x, y, s", "failure");
     }
-    if (h2d(c, w->sol_x, sol->x, (size_t)n) || h2d(c, w->sol_y, sol->y + w->row0, (size_t)m) ||
+    const double *xsrc = sol->x;
+    if (w->dist) {  // this rank's columns of the caller's full x
+      w->x_loc.resize((size_t)n);
+      for (int j = 0; j < n; ++j) w->x_loc[(size_t)j] = sol->x[w->loc2glob[(size_t)j]];
+      xsrc = w->x_loc.data();
+    }
+    if (h2d(c, w->sol_x, xsrc, (size_t)n) || h2d(c, w->sol_y, sol->y + w->row0, (size_t)m) ||
         h2d(c, w->sol_s, sol->s + w->row0, (size_t)m))
-      return failure(w, m_out, n, sol, info, SCS_FAILED, "warm-start upload", "failure");
+      return failure(w, m_out, n_out, sol, info, SCS_FAILED, "warm-start upload", "failure");
     k_warm_start<<<ew_grid(c, l), kThreads, 0, st>>>(w->v, w->sol_x, w->sol_y, w->sol_s, w->D, w->E, w->diag_r, n, m,
                                                      w->primal_scale, w->dual_scale);
   } else {
     k_cold_start<<<ew_grid(c, l), kThreads, 0, st>>>(w->v, l);
   }
   c.launches++;
-  if (update_work_cache(w)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in update_work_cache", "failure");
-  if (stgs->verbose) print_header();
+  if (update_work_cache(w)) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in update_work_cache", "failure");
+  // row-partitioned mode: `vwork` (same on every rank) decides whether the verbose-only residual passes --
+  // which carry collectives -- run; `vprint` (rank 0 only) whether their results are printed
+  const bool vwork = stgs->verbose || w->verbose_collective, vprint = stgs->verbose || w->print_rank0;
+  if (vprint) print_header();
 
   const int gl = ew_grid(c, l);
   const bool accel = w->has_aa;
@@ -1599,7 +1744,7 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
     if (accel && i > 0 && i % interval == 0) {
       k_stamp<<<1, 1, 0, st>>>(c.S, -1);
       if (w->aa.apply(w->v, w->v_prev, &c.S->vnorm2))
-        return failure(w, m_out, n, sol, info, SCS_FAILED, "error in aa_apply", "failure");
+        return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in aa_apply", "failure");
       k_stamp<<<1, 1, 0, st>>>(c.S, 2);
       c.launches += 2;
       w->n_aa++;
@@ -1608,21 +1753,21 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
     //      enqueued on the stream with the CG loop driven from the host
     if (w->use_graph) {
       if (cudaGraphLaunch(w->gexec, st) != cudaSuccess)
-        return failure(w, m_out, n, sol, info, SCS_FAILED, "error launching the iteration graph", "failure");
+        return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error launching the iteration graph", "failure");
       c.launches += w->graph_launches;
       c.spmv_calls += w->graph_spmv;
     } else {
       if (enqueue_front_head(w, CgCtl{}) || w->ls.solve_dev_loop(w->u_t, 0) || enqueue_front_tail(w))
-        return failure(w, m_out, n, sol, info, SCS_FAILED, "error in project_lin_sys / project_cones", "failure");
+        return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in project_lin_sys / project_cones", "failure");
     }
 
     const bool check = (i % kConvergedInterval == 0);
-    const bool print = stgs->verbose && (i % kPrintInterval == 0);
+    const bool print = vwork && (i % kPrintInterval == 0);
     if (check || print) {
-      k_post<1><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, n, l, w->own_x, stgs->alpha, c.red, c.S);
+      k_post<1><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, n, l, w->cnt_lo, stgs->alpha, c.red, c.S);
       c.launches++;
-      if (check && g_int_detected && !w->dist) return failure(w, m_out, n, sol, info, SCS_SIGINT, "interrupted", "interrupted");
-      if (populate_residuals(w, i)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in residuals", "failure");
+      if (check && g_int_detected && !w->dist) return failure(w, m_out, n_out, sol, info, SCS_SIGINT, "interrupted", "interrupted");
+      if (populate_residuals(w, i)) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in residuals", "failure");
       w->n_checks++;
       if (check) {
         if ((info->status_val = has_converged(w)) != 0) break;
@@ -1631,48 +1776,48 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
           break;
         }
       }
-      if (print) print_summary(w, i, t0);
+      if (print && vprint) print_summary(w, i, t0);
       if (stgs->adaptive_scale && i == w->r_o.last_iter) {
-        if (update_scale(w, i) < 0) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in update_scale", "failure");
+        if (update_scale(w, i) < 0) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in update_scale", "failure");
       }
-      k_post<2><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, n, l, w->own_x, stgs->alpha, c.red, c.S);
-      if (dist_finish(c, 1, 0, FinPost{})) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in the dual step", "failure");
+      k_post<2><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, n, l, w->cnt_lo, stgs->alpha, c.red, c.S);
+      if (dist_finish(c, 1, 0, FinPost{})) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in the dual step", "failure");
       c.launches++;
     } else {
-      k_post<0><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, n, l, w->own_x, stgs->alpha, c.red, c.S);
-      if (dist_finish(c, 1, 0, FinPost{})) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in the dual step", "failure");
+      k_post<0><<<gl, kThreads, 0, st>>>(w->v, w->rsk, w->u, w->u_t, w->diag_r, n, l, w->cnt_lo, stgs->alpha, c.red, c.S);
+      if (dist_finish(c, 1, 0, FinPost{})) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in the dual step", "failure");
       c.launches++;
     }
     // ---- AA safeguard (scs.c:1386-1394); the aa_norm > 0 gate is evaluated on the device
     if (accel && i > 0 && i % interval == 0) {
       k_stamp<<<1, 1, 0, st>>>(c.S, -1);
       if (w->aa.safeguard(w->v, w->v_prev, &c.S->vnorm2, &c.S->aa_rejected, &c.S->aa_accepted))
-        return failure(w, m_out, n, sol, info, SCS_FAILED, "error in aa_safeguard", "failure");
+        return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in aa_safeguard", "failure");
       k_stamp<<<1, 1, 0, st>>>(c.S, 2);
       c.launches += 2;
     }
     // ---- CSV trace, after the scale update so that the extra residual pass does not touch the
     //      algorithm (scs.c:1396-1401)
-    if (csv && csv_log(w, i, t0)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in the CSV trace", "failure");
+    if (csv && csv_log(w, i, t0)) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in the CSV trace", "failure");
   }
-  if (csv && csv_log(w, i, t0)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in the CSV trace", "failure");
+  if (csv && csv_log(w, i, t0)) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in the CSV trace", "failure");
   if (w->mk_open) mark_close(w, i);
   w->mark_begin = w->mark_end = -1;
   w->admm_iters += i;
-  if (stgs->verbose) {
-    if (populate_residuals(w, i)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in residuals", "failure");
-    print_summary(w, i, t0);
+  if (vwork) {
+    if (populate_residuals(w, i)) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in residuals", "failure");
+    if (vprint) print_summary(w, i, t0);
   }
   // ---- finalize (scs.c:874-924)
-  if (!sol->x) sol->x = (double *)calloc(n, sizeof(double));
+  if (!sol->x) sol->x = (double *)calloc(n_out, sizeof(double));
   if (!sol->y) sol->y = (double *)calloc(m_out, sizeof(double));
   if (!sol->s) sol->s = (double *)calloc(m_out, sizeof(double));
   k_finalize_sol<<<ew_grid(c, n + m), kThreads, 0, st>>>(w->sol_x, w->sol_y, w->sol_s, w->u, w->rsk, w->D, w->E, n, m,
                                                          w->primal_scale, w->dual_scale, c.red, c.S);
   c.launches++;
-  if (dist_finish(c, 1, 2, FinSol{})) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in finalize", "failure");
-  if (populate_residuals(w, i)) return failure(w, m_out, n, sol, info, SCS_FAILED, "error in residuals", "failure");
-  if (c.fetch_scalars()) return failure(w, m_out, n, sol, info, SCS_FAILED, "fetch", "failure");
+  if (dist_finish(c, 1, 2, FinSol{})) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in finalize", "failure");
+  if (populate_residuals(w, i)) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in residuals", "failure");
+  if (c.fetch_scalars()) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "fetch", "failure");
   w->ls.tot_cg_its = c.S_host->cg_its_total;
   const double nm_s = c.S_host->fin[0], nm_y = c.S_host->fin[1], sty = c.S_host->fin[2];
   const HostResid &r = w->r_o;
@@ -1742,18 +1887,24 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
       if (cudaMemsetAsync(w->gather, 0, sizeof(double) * (size_t)m_out, st) != cudaSuccess ||
           cudaMemcpyAsync(w->gather + w->row0, src, sizeof(double) * (size_t)m, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
           dist_allreduce(c, w->gather, (size_t)m_out, 0) || d2h(c, dst, w->gather, (size_t)m_out) || c.sync())
-        return failure(w, m_out, n, sol, info, SCS_FAILED, "solution gather", "failure");
+        return failure(w, m_out, n_out, sol, info, SCS_FAILED, "solution gather", "failure");
     }
-    if (d2h(c, sol->x, w->sol_x, (size_t)n) || c.sync())
-      return failure(w, m_out, n, sol, info, SCS_FAILED, "solution download", "failure");
+    // x: every rank scatters the columns it counts (rank 0: shared + private, others: private) into a
+    // zeroed full-length buffer; the sum over the ranks is the full x
+    if (cudaMemsetAsync(w->gather, 0, sizeof(double) * (size_t)w->n_total, st) != cudaSuccess)
+      return failure(w, m_out, n_out, sol, info, SCS_FAILED, "solution gather", "failure");
+    k_scatter_cols<<<ew_grid(c, n), kThreads, 0, st>>>(w->gather, w->sol_x, w->d_loc2glob, w->cnt_lo, n);
+    c.launches++;
+    if (dist_allreduce(c, w->gather, (size_t)w->n_total, 0) || d2h(c, sol->x, w->gather, (size_t)w->n_total) || c.sync())
+      return failure(w, m_out, n_out, sol, info, SCS_FAILED, "solution download", "failure");
   } else if (d2h(c, sol->x, w->sol_x, (size_t)n) || d2h(c, sol->y, w->sol_y, (size_t)m) ||
              d2h(c, sol->s, w->sol_s, (size_t)m) || c.sync())
-    return failure(w, m_out, n, sol, info, SCS_FAILED, "solution download", "failure");
+    return failure(w, m_out, n_out, sol, info, SCS_FAILED, "solution download", "failure");
   info->solve_time = ms_since(t0);
   info->lin_sys_time = c.S_host->phase_ns[0] * 1e-6;  // %globaltimer phase clocks, see phase_lap()
   info->cone_time = c.S_host->phase_ns[1] * 1e-6;
   info->accel_time = c.S_host->phase_ns[2] * 1e-6;
-  if (stgs->verbose) print_footer(info);
+  if (vprint) print_footer(info);
   end_interrupt_listener();
   return info->status_val;
 }
@@ -1784,8 +1935,31 @@ extern "C" scs_int scs_b200_dist_partition(const ScsData *d, const ScsCone *k, s
     return 0;
   }
   if (partition_rows(d, k, rank, world, lp)) return -1;
-  out[0] = lp.row0; out[1] = lp.m; out[2] = lp.Ap[(size_t)d->n]; out[3] = lp.k.z; out[4] = lp.k.l; out[5] = lp.k.bsize;
+  out[0] = lp.row0; out[1] = lp.m; out[2] = lp.Ap[(size_t)lp.n_loc]; out[3] = lp.k.z; out[4] = lp.k.l; out[5] = lp.k.bsize;
   out[6] = lp.k.qsize; out[7] = lp.k.ssize; out[8] = lp.k.cssize; out[9] = lp.k.ep; out[10] = lp.k.ed; out[11] = lp.k.psize;
+  return 0;
+}
+
+// Host-only: the local problem rank `rank` of `world` would build (CPU test tier).  sizes = {row0, m_loc,
+// n_shared, n_loc, nnz(A_loc), nnz(P_loc)}; every array pointer may be NULL (first call: sizes only).
+extern "C" scs_int scs_b200_dist_local(const ScsData *d, const ScsCone *k, scs_int rank, scs_int world, scs_int sizes[6],
+                                       scs_int *loc2glob, scs_int *Ap, scs_int *Ai, scs_float *Ax, scs_int *Pp,
+                                       scs_int *Pi, scs_float *Px, scs_float *c_loc) {
+  if (!d || !k || !sizes || !d->A || world < 1 || rank < 0 || rank >= world) return -1;
+  LocalProblem lp;
+  if (partition_rows(d, k, rank, world, lp)) return -1;
+  const int nl = lp.n_loc, nzA = lp.Ap[(size_t)nl], nzP = d->P ? lp.Pp[(size_t)nl] : 0;
+  sizes[0] = lp.row0; sizes[1] = lp.m; sizes[2] = lp.n_sh; sizes[3] = nl; sizes[4] = nzA; sizes[5] = nzP;
+  if (loc2glob) memcpy(loc2glob, lp.loc2glob.data(), sizeof(int) * (size_t)nl);
+  if (Ap) memcpy(Ap, lp.Ap.data(), sizeof(int) * ((size_t)nl + 1));
+  if (Ai && nzA) memcpy(Ai, lp.Ai.data(), sizeof(int) * (size_t)nzA);
+  if (Ax && nzA) memcpy(Ax, lp.Ax.data(), sizeof(double) * (size_t)nzA);
+  if (d->P) {
+    if (Pp) memcpy(Pp, lp.Pp.data(), sizeof(int) * ((size_t)nl + 1));
+    if (Pi && nzP) memcpy(Pi, lp.Pi.data(), sizeof(int) * (size_t)nzP);
+    if (Px && nzP) memcpy(Px, lp.Px.data(), sizeof(double) * (size_t)nzP);
+  }
+  if (c_loc) memcpy(c_loc, lp.c.data(), sizeof(double) * (size_t)nl);
   return 0;
 }
 

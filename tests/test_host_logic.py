@@ -293,3 +293,69 @@ def test_tiled_plan_covers_every_cell_once_and_balances(seed, nrb, ncb, sms):
         cell = np.maximum(384.0 * hg[hg > 0] + 8.0 * TC, 70000.0)
         assert abs(cost.sum() - (cell[np.isin(np.nonzero(hg)[0], tiled_bins)].sum() + 16.0 * TR * len(items))) < 1e-6 * cost.sum()
         assert cost.max() <= cost.sum() / len(cost) + 3 * cell.max() + 2 * 16.0 * TR * max(1, items.shape[0] // len(cost) + 1)
+
+
+def _locals(data, K, world):
+    import scipy.sparse as sp
+    from scs_python_b200 import _scs_b200 as B
+    A = sp.csc_matrix(data["A"]); A.sort_indices()
+    P = data.get("P")
+    args = [A.shape, A.data, A.indices.astype(np.int32), A.indptr.astype(np.int32)]
+    if P is not None:
+        P = sp.triu(sp.csc_matrix(P), format="csc"); P.sort_indices()
+        args += [P.data, P.indices.astype(np.int32), P.indptr.astype(np.int32)]
+    else:
+        args += [None, None, None]
+    return A, P, [B.dist_local(*args, data["b"], data["c"], K, r, world) for r in range(world)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("kind", ["lasso", "cone_qp", "coupled_P"])
+def test_column_classification_reassembles_the_problem(world, kind):
+    """Row-partitioned mode, host side: every rank keeps its rows and the columns they touch, in the local
+    order [shared | private].  Shared columns are the same on every rank, every private column belongs to
+    exactly one rank and has no entry outside that rank's rows, P restricted to a rank's columns loses
+    nothing, and scattering the local blocks back gives A, P and c exactly."""
+    import scipy.sparse as sp
+    from scs_python_b200 import problems as Pm
+    if kind == "lasso":
+        data, K, _ = Pm.lasso(400, 800, 10, seed=1)
+    elif kind == "cone_qp":
+        data, K, _ = Pm.random_cone_qp(seed=3, n=200, l=300, nq=30, q=7, ep=20, density=0.04)
+    else:  # P with off-diagonal couplings: coupled columns must stay shared
+        data, K, _ = Pm.lasso(300, 600, 8, seed=2)
+        n = data["A"].shape[1]
+        rng = np.random.RandomState(0)
+        i, j = rng.randint(0, n, 40), rng.randint(0, n, 40)
+        C_ = sp.csc_matrix((np.ones(40), (np.minimum(i, j), np.maximum(i, j))), shape=(n, n))
+        data["P"] = sp.triu(sp.csc_matrix(data["P"]) + C_ + sp.eye(n), format="csc")
+    A, P, loc = _locals(data, K, world)
+    m, n = A.shape
+    shared = loc[0]["loc2glob"][:loc[0]["n_sh"]]
+    seen = np.zeros(n, dtype=int)
+    seen[shared] += 1
+    Afull = sp.lil_matrix((m, n))
+    row = 0
+    for r, L in enumerate(loc):
+        l2g, nsh = L["loc2glob"], L["n_sh"]
+        assert np.array_equal(l2g[:nsh], shared) and np.all(np.diff(l2g[:nsh]) > 0) and np.all(np.diff(l2g[nsh:]) > 0)
+        seen[l2g[nsh:]] += 1
+        assert L["row0"] == row
+        row += L["m"]
+        Al = sp.coo_matrix(L["A"])
+        Afull[Al.row + L["row0"], l2g[Al.col]] = Al.data
+        assert np.array_equal(L["c"], data["c"][l2g])
+        # a private column has no entry outside this rank's rows
+        priv = l2g[nsh:]
+        if len(priv):
+            assert A[:, priv].nnz == L["A"][:, nsh:].nnz
+        if P is not None:
+            Pl = sp.coo_matrix(L["P"])
+            assert np.all(Pl.row <= Pl.col)  # still upper triangular in the local order
+            ref = sp.coo_matrix(P[:, l2g][l2g, :])
+            assert abs(sp.csc_matrix(L["P"]) - sp.csc_matrix(ref)).sum() == 0
+            assert P[:, l2g].nnz == L["P"].nnz  # no entry of these columns of P falls outside the local set
+    assert row == m and np.all(seen == 1)
+    assert abs(sp.csc_matrix(Afull) - A).sum() == 0
+    if world > 1 and kind == "lasso":  # the y block of LASSO (identity columns) is private: less than half is shared
+        assert len(shared) < 0.6 * n
