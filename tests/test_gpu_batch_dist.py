@@ -140,15 +140,3 @@ def test_batch_large_count_properties(scsb):
     assert all(s["info"]["status_val"] == 1 for s in sols)
     for i in range(0, 1024, 97):
         helpers.verify_solution(probs[i][0], probs[i][1], sols[i], 1e-4, 1e-4)
-
-
-def test_row_partitioned_two_gpus(gpu):
-    """2-rank NCCL run of tests/dist_gpu_check.py: the row-partitioned solve agrees with the
-    single-GPU solve on cone QP / LASSO / SOCP / SDP (status, objectives 1e-6, iterates 1e-4)."""
-    if gpu < 2:
-        pytest.skip("needs 2 GPUs on the box (the CPU tier covers the partition logic under gloo)")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29671",
-                        os.path.join(ROOT, "tests", "dist_gpu_check.py")],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert r.returncode == 0 and "dist check ok" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
