@@ -140,6 +140,7 @@ struct EpiG {
 struct FinCgStart {
   CgCtl ctl;
   __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    if (S->cg_done) return;  // deferred call (row-partitioned mode) after a kernel that exited at once
     S->ztr = o[0];
     S->norm_r = o[1];
     const int done = (o[1] < fmax(S->cg_tol, 1e-12)) ? 1 : 0;
@@ -151,6 +152,7 @@ struct FinCgStart {
 struct FinCgUpdate {
   CgCtl ctl;
   __device__ __forceinline__ void operator()(double *o, DevScalars *S) const {
+    if (S->cg_done) return;  // deferred call (row-partitioned mode) after a kernel that exited at once
     const double ztr_prev = S->ztr;
     const int its = S->cg_its + 1;
     S->cg_its = its;
