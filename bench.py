@@ -173,7 +173,8 @@ def _reduce(td, local, x, op):
     if td is None:
         return float(x)
     import torch
-    t = torch.tensor([float(x)], dtype=torch.float64, device=torch.device("cuda", local))
+    dev = local if isinstance(local, torch.device) else torch.device("cuda", local)
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
     td.all_reduce(t, op=getattr(td.ReduceOp, op))
     return float(t.item())
 

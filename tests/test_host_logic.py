@@ -55,19 +55,26 @@ def test_gen_feasible_is_feasible():
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, %(root)r)
+import numpy as np
 import torch, torch.distributed as td
 import bench
 td.init_process_group(backend="gloo")
 rank, world = td.get_rank(), td.get_world_size()
 dev = torch.device("cpu")
-# every rank owns its own problem instance (seed + rank): no data-path collective
-data, cone, desc = bench.workload(0.001, seed=rank)
+# N > 1 is strong scaling: every rank holds the SAME problem and keeps its block of rows / columns
+data, cone = bench.workload(0.001, seed=0)
+from scs_python_b200 import _scs_b200 as B
+A, P = data["A"], data["P"]
+L = B.dist_local(A.shape, A.data, A.indices.astype(np.int32), A.indptr.astype(np.int32), P.data,
+                 P.indices.astype(np.int32), P.indptr.astype(np.int32), data["b"], data["c"], cone, rank, world)
+rows = bench.sum_over_ranks(td, dev, L["m"])
+priv = bench.sum_over_ranks(td, dev, len(L["loc2glob"]) - L["n_sh"])
 iters, ms = 25 * 4, 10.0 * (rank + 1)
-tot = bench.sum_over_ranks(td, dev, iters)
 mx = bench.max_over_ranks(td, dev, ms)
 if rank == 0:
     import json
-    print(json.dumps(dict(world=world, total_iters=tot, max_ms=mx, value=tot / (mx * 1e-3), nnz=desc["nnz_A"])))
+    print(json.dumps(dict(world=world, rows=rows, m=int(A.shape[0]), n=int(A.shape[1]), n_sh=int(L["n_sh"]), priv=priv,
+                          max_ms=mx, value=iters / (mx * 1e-3))))
 td.barrier()
 td.destroy_process_group()
 '''
@@ -82,8 +89,9 @@ def test_rank_sharding_world_size_2_gloo(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
-    assert out["world"] == 2 and out["total_iters"] == 200 and out["max_ms"] == 20.0
-    assert abs(out["value"] - 200 / 0.020) < 1e-6   # whole-job iterations / slowest rank
+    assert out["world"] == 2 and out["max_ms"] == 20.0
+    assert out["rows"] == out["m"] and out["n_sh"] + out["priv"] == out["n"]  # the ranks' blocks tile the problem
+    assert abs(out["value"] - 100 / 0.020) < 1e-6   # strong scaling: the job's iterations / slowest rank
 
 
 def test_bench_reference_arm_runs_on_cpu():
