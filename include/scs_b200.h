@@ -212,6 +212,12 @@ void scs_b200_finish_cone(ScsB200ConeWork *c);
 double scs_b200_bench_proj_cone(ScsB200ConeWork *c, const scs_float *x0, const scs_float *x1,
                                 scs_float step, scs_int reps, scs_int warmup, double *sweeps_out);
 
+/* root_plus, S/src/scs.c:667-688 (static there; exercised by S/test/problems/test_root_plus.h): the device
+ * kernel of the ADMM loop on host buffers.  g, p, mu, r: nm entries; tau_scale = diag_r[n+m]; eta = v[n+m].
+ * Returns tau (NaN on failure). */
+scs_float scs_b200_root_plus(const scs_float *g, const scs_float *p, const scs_float *mu, const scs_float *r,
+                             scs_int nm, scs_float tau_scale, scs_float eta);
+
 /* SCS(accum_by_a / accum_by_atrans / accum_by_p), scs_matrix.c:135-199: y += A x etc.
  * A is CSC; P upper-triangular CSC.  Host buffers. Returns 0 on success. */
 scs_int scs_b200_accum_by_a(const ScsMatrix *A, const scs_float *x, scs_float *y);

@@ -130,6 +130,8 @@ lib.scs_b200_dist_partition.argtypes = [C.POINTER(ScsData), C.POINTER(ScsCone), 
 lib.scs_b200_dist_local.restype = c_int
 lib.scs_b200_dist_local.argtypes = [C.POINTER(ScsData), C.POINTER(ScsCone), c_int, c_int, C.POINTER(c_int * 6), p_int,
                                     p_int, p_int, p_double, p_int, p_int, p_double, p_double]
+lib.scs_b200_root_plus.restype = c_double
+lib.scs_b200_root_plus.argtypes = [p_double, p_double, p_double, p_double, c_int, c_double, c_double]
 lib.scs_b200_lin_sys_cg_its.restype = c_int
 lib.scs_b200_lin_sys_cg_its.argtypes = [C.c_void_p]
 lib.scs_b200_init_cone.restype = C.c_void_p

@@ -123,6 +123,11 @@ struct Ctx {
   int cnt_lo = 0;  // reductions over n-space count [cnt_lo, n): 0 on rank 0, n_sh on the others
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // side stream of a product that forks (tiled.cuh: the short-row pass runs in the shadow of the streaming
+  // kernel); forked and joined with events, so it follows `stream` into a graph capture
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_ready() const { return side != nullptr; }
   RedWs red{nullptr, nullptr, 0};
   DevScalars *S = nullptr;       // device
   DevScalars *S_host = nullptr;  // pinned mirror
@@ -149,6 +154,9 @@ struct Ctx {
     CUDA_OK(cudaMallocHost(&S_host, sizeof(DevScalars)));
     memset(S_host, 0, sizeof(DevScalars));
     CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     return 0;
   }
   void destroy() {
@@ -158,6 +166,10 @@ struct Ctx {
     if (S) cudaFree(S);
     if (S_host) cudaFreeHost(S_host);
     if (ev) cudaEventDestroy(ev);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
+    side = nullptr; ev_fork = ev_join = nullptr;
     if (own_stream && stream) cudaStreamDestroy(stream);
     red = RedWs{nullptr, nullptr, 0};
     S = nullptr; S_host = nullptr; ev = nullptr; stream = nullptr;

@@ -1963,6 +1963,34 @@ extern "C" scs_int scs_b200_dist_local(const ScsData *d, const ScsCone *k, scs_i
   return 0;
 }
 
+// root_plus (scs.c:667-688) on host buffers: the device kernel of the ADMM loop (k_rootplus + FinRootPlus) on
+// p = u_t, mu = v, g, r = diag_r (nm entries each), tau_scale = diag_r[nm], eta = v[nm].  Parity-test surface
+// for the reference's known-answer test S/test/problems/test_root_plus.h.
+extern "C" scs_float scs_b200_root_plus(const scs_float *g, const scs_float *p, const scs_float *mu, const scs_float *r,
+                                        scs_int nm, scs_float tau_scale, scs_float eta) {
+  if (!g || !p || !mu || !r || nm <= 0) return NAN;
+  Ctx c;
+  if (c.init(current_device())) return NAN;
+  double *dg = nullptr, *dp = nullptr, *dmu = nullptr, *dr = nullptr;
+  double tau = NAN;
+  do {
+    if (dev_alloc(&dg, (size_t)nm) || dev_alloc(&dp, (size_t)nm) || dev_alloc(&dmu, (size_t)nm + 1) ||
+        dev_alloc(&dr, (size_t)nm + 1))
+      break;
+    if (h2d(c, dg, g, (size_t)nm) || h2d(c, dp, p, (size_t)nm) || h2d(c, dmu, mu, (size_t)nm) || h2d(c, dmu + nm, &eta, 1) ||
+        h2d(c, dr, r, (size_t)nm) || h2d(c, dr + nm, &tau_scale, 1))
+      break;
+    const int one = kFeasibleIters;  // iteration >= FEASIBLE_ITERS: the quadratic is evaluated (scs.c:722-724)
+    if (cudaMemcpyAsync(&c.S->iter, &one, sizeof(int), cudaMemcpyHostToDevice, c.stream) != cudaSuccess) break;
+    k_rootplus<<<ew_grid(c, nm), kThreads, 0, c.stream>>>(dp, dmu, dg, dr, 0, nm, 0, c.red, c.S);
+    if (cudaGetLastError() != cudaSuccess || c.fetch_scalars()) break;
+    tau = c.S_host->tau;
+  } while (0);
+  dev_free(dg); dev_free(dp); dev_free(dmu); dev_free(dr);
+  c.destroy();
+  return tau;
+}
+
 // ------------------------------------------------------------------ measurement -------
 extern "C" scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out) {
   if (!w || !out) return -1;

@@ -100,13 +100,19 @@ __global__ void __launch_bounds__(kThreads) k_tl_pad(unsigned *__restrict__ pk, 
 __global__ void __launch_bounds__(kThreads)
 k_tl_scatter(const unsigned *__restrict__ skey, const unsigned *__restrict__ sval, long long total, long long nnz1,
              const int *__restrict__ sstart, const int *__restrict__ gbase, const int *__restrict__ rowof, CsrDev M1,
-             CsrDev M2, unsigned *__restrict__ pk, double *__restrict__ val) {
+             CsrDev M2, unsigned *__restrict__ pk, double *__restrict__ val, int lane_perm) {
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
     const unsigned seg = skey[p] >> 4;
     const unsigned src = sval[p];
     const int k = (int)(p - sstart[seg]);
     const int g0 = gbase[seg], G = gbase[seg + 1] - g0;
-    const int grp = k % G, lane = k / G;
+    // entry k of the segment (sorted by accumulator bank pair, then row-major) goes to group k mod G; the
+    // chunk k div G picks the lane.  Consecutive chunks hold the same or neighbouring bank pairs, and a
+    // 64-bit shared-memory access is served one half-warp at a time, so consecutive chunks alternate between
+    // the two half-warps: inside a half-warp the lanes of a group are then two chunks (~2G sorted entries, more
+    // than one bank-pair class) apart.
+    const int grp = k % G, chunk = k / G;
+    const int lane = lane_perm ? (((chunk & 1) << 4) | (chunk >> 1)) : chunk;
     int col;
     double v;
     if ((long long)src < nnz1) { col = M1.idx[src]; v = M1.val[src]; }
@@ -292,6 +298,8 @@ extern "C" scs_int scs_b200_tiled_plan(scs_int nrows, scs_int ncb, const scs_int
 void TiledOp::destroy() {
   dev_free(d.items); dev_free(d.cta_off); dev_free(d.seq); dev_free(d.cta_seq_off); dev_free(d.gbase);
   dev_free(d.pk); dev_free(d.val); dev_free(d.partial); dev_free(d.binfo); dev_free(d.prof);
+  dev_free(d.dbins); dev_free(d.ydir);
+  d.ndbins = 0;
   has_tiled = false;
   ok = false;
 }
@@ -365,7 +373,9 @@ int TiledOp::build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force) {
     k_tl_iota<<<grid, kThreads, 0, st>>>(sv, total);
     if (cub::DeviceRadixSort::SortPairs(tmp, tb3, key, key2, sv, sv2, (int)total, 0, bits, st) != cudaSuccess) break;
     k_tl_pad<<<grid, kThreads, 0, st>>>(d.pk, d.val, slots);
-    k_tl_scatter<<<grid, kThreads, 0, st>>>(key2, sv2, total, nnz1, sstart, d.gbase, rowof, m1, m2 ? *m2 : m1, d.pk, d.val);
+    const char *lp_env = getenv("SCS_B200_TILED_LANE_PERM");  // "0": the round-1 dealing (comparison runs)
+    k_tl_scatter<<<grid, kThreads, 0, st>>>(key2, sv2, total, nnz1, sstart, d.gbase, rowof, m1, m2 ? *m2 : m1, d.pk, d.val,
+                                            (lp_env && atoi(lp_env) == 0) ? 0 : 1);
     k_tl_flag_empty<<<grid, kThreads, 0, st>>>(cnt, d.gbase, nseg, d.pk);
     c.launches += 4;
     lap("sort+scatter");
@@ -402,6 +412,27 @@ int TiledOp::build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force) {
         cudaMemcpyAsync(d.cta_seq_off, h_seq_off.data(), sizeof(int) * h_seq_off.size(), cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(d.binfo, h_binfo.data(), sizeof(int2) * h_binfo.size(), cudaMemcpyHostToDevice, st) != cudaSuccess)
       break;
+    {  // short-row bins: their list, and the raw-product scratch of the side-stream pass
+      std::vector<int> db;
+      for (int rb = 0; rb < nrb; ++rb) {
+        const int r0 = rb * kTR, r1 = std::min(nrows, r0 + kTR);
+        const bool empty = p1[(size_t)r1] == p1[(size_t)r0] && (!m2 || p2[(size_t)r1] == p2[(size_t)r0]);
+        if (h_binfo[(size_t)rb].y == 0 && !empty) db.push_back(rb);
+      }
+      const char *e = getenv("SCS_B200_TILED_SIDE");  // "0": the epilogue pass multiplies the short rows out itself
+      const bool side_on = !(e && atoi(e) == 0);
+      d.ndbins = 0;
+      if (side_on && nitems > 0 && !db.empty()) {
+        if (dev_alloc(&d.dbins, db.size()) || dev_alloc_zero(&d.ydir, (size_t)nrows, st) ||
+            cudaMemcpyAsync(d.dbins, db.data(), sizeof(int) * db.size(), cudaMemcpyHostToDevice, st) != cudaSuccess)
+          break;
+        d.ndbins = (int)db.size();
+      }
+    }
+    {
+      const char *e = getenv("SCS_B200_TILED_U");  // groups per register buffer of the streaming kernel: 8 or 12
+      variant = (e && atoi(e) == 12) ? 1 : 0;
+    }
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) break;
     lap("plan+upload");
     if (verbose)

@@ -71,6 +71,11 @@ struct TiledDev {
   double *val = nullptr;       // values, [group][lane]
   double *partial = nullptr;   // scratch: one slot of kTR doubles per piece
   int2 *binfo = nullptr;       // per row bin: {first slot, pieces}; pieces == 0: short-row bin (epilogue pass)
+  // short-row bins multiplied out by tiled_direct_kernel on a side stream while the streaming kernel runs:
+  // the list of those bins and their raw products (indexed by row); ydir == null: the epilogue pass does it
+  int *dbins = nullptr;
+  int ndbins = 0;
+  double *ydir = nullptr;
   unsigned long long *prof = nullptr;  // per CTA of the last launch: %globaltimer at start, at end, ns spent streaming
 };
 
@@ -83,6 +88,7 @@ struct TiledOp {
   std::vector<double> cta_cost;  // modelled cost of every CTA's item list (host plan)
   std::vector<int> cta_items;
   bool has_tiled = false;  // false: every row bin is a short-row bin (the epilogue pass does it all)
+  int variant = 0;         // streaming-kernel variant (tiled_kernel<variant>: groups in flight per warp)
   CsrDev m1, m2;
   bool has2 = false;
   // Build from CSR(M1) [and CSR(M2) with the same row count, acting on a second vector]:
@@ -141,7 +147,8 @@ __device__ __forceinline__ unsigned atom_add_acq_rel(unsigned *p, unsigned v) {
 
 // Streaming kernel: partial sums of every work item into its scratch slot.  kt_cat >= 0: this launch
 // opens the in-region timing window of that SpMV category (common.cuh kt_begin).
-template <int kVariant>  // (a template only for its linkage: the header is included by several translation units)
+// kVariant: groups of 32 entries a warp keeps in flight = 2 x U with U = 8 (variant 0) or 12 (variant 1)
+template <int kVariant>
 __global__ void __launch_bounds__(kTThreads, 1)
 tiled_kernel(TiledDev T, const double *__restrict__ x1, const double *x2, DevScalars *S, int kt_cat,
              const int *skip) {
@@ -193,7 +200,7 @@ tiled_kernel(TiledDev T, const double *__restrict__ x1, const double *x2, DevSca
       }
     }
   };
-  constexpr int U = 8;
+  constexpr int U = kVariant == 0 ? 8 : 12;
   for (int ii = i0; ii < i1; ++ii) {
     const TItem im = T.items[ii];
     const unsigned long long t_item = threadIdx.x == 0 ? gtimer() : 0ull;
@@ -283,7 +290,7 @@ tiled_epilogue_kernel(TiledDev T, CsrDev m1, CsrDev m2, int has2, const double *
       if (row < T.nrows) {
         bi[k] = T.binfo[row / kTR];
         pre[k] = epi.load(row);
-        if (bi[k].y == 0) {
+        if (bi[k].y == 0 && T.ydir == nullptr) {
           sA[k] = m1.ptr[row]; eA[k] = m1.ptr[row + 1];
           if (has2) { sB[k] = m2.ptr[row]; eB[k] = m2.ptr[row + 1]; }
         }
@@ -295,8 +302,12 @@ tiled_epilogue_kernel(TiledDev T, CsrDev m1, CsrDev m2, int has2, const double *
       double a = 0.0;
       if (row < T.nrows) {
         if (bi[k].y == 0) {
-          for (int j = sA[k]; j < eA[k]; ++j) a = fma(__ldcs(m1.val + j), __ldg(x1 + __ldcs(m1.idx + j)), a);
-          for (int j = sB[k]; j < eB[k]; ++j) a = fma(__ldcs(m2.val + j), __ldg(x2 + __ldcs(m2.idx + j)), a);
+          if (T.ydir != nullptr) {
+            a = __ldcs(T.ydir + row);  // multiplied out by tiled_direct_kernel while the streaming kernel ran
+          } else {
+            for (int j = sA[k]; j < eA[k]; ++j) a = fma(__ldcs(m1.val + j), __ldg(x1 + __ldcs(m1.idx + j)), a);
+            for (int j = sB[k]; j < eB[k]; ++j) a = fma(__ldcs(m2.val + j), __ldg(x2 + __ldcs(m2.idx + j)), a);
+          }
         } else {
           const double *src = T.partial + (size_t)bi[k].x * kTR + (row % kTR);
           for (int p = 0; p < bi[k].y; ++p) a += __ldcs(src + (size_t)p * kTR);
@@ -313,8 +324,46 @@ tiled_epilogue_kernel(TiledDev T, CsrDev m1, CsrDev m2, int has2, const double *
   epi.finish(st, ws, S);
 }
 
+// Short-row bins (identity / bound blocks) multiplied out row by row straight from the CSR arrays: raw
+// products into T.ydir.  Launched on the workspace's side stream so that it runs in the shadow of the
+// streaming kernel (which leaves 3/4 of every SM's thread slots idle by construction).
+template <int kDummy>
+__global__ void __launch_bounds__(kThreads, 8)  // <= 32 registers: two of these CTAs fit next to a streaming CTA
+tiled_direct_kernel(TiledDev T, CsrDev m1, CsrDev m2, int has2, const double *__restrict__ x1, const double *x2,
+                    const int *skip) {
+  if (skip != nullptr && *skip != 0) return;
+  const long long total = (long long)T.ndbins * kTR;
+  constexpr int EB = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += stride * EB) {
+    int row[EB], sA[EB], eA[EB], sB[EB], eB[EB];
+#pragma unroll
+    for (int k = 0; k < EB; ++k) {
+      const long long t = base + k * stride;
+      row[k] = -1; sA[k] = eA[k] = sB[k] = eB[k] = 0;
+      if (t < total) {
+        const int r = T.dbins[t / kTR] * kTR + (int)(t % kTR);
+        if (r < T.nrows) {
+          row[k] = r;
+          sA[k] = m1.ptr[r]; eA[k] = m1.ptr[r + 1];
+          if (has2) { sB[k] = m2.ptr[r]; eB[k] = m2.ptr[r + 1]; }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < EB; ++k) {
+      if (row[k] < 0) continue;
+      double a = 0.0;
+      for (int j = sA[k]; j < eA[k]; ++j) a = fma(__ldcs(m1.val + j), __ldg(x1 + __ldcs(m1.idx + j)), a);
+      for (int j = sB[k]; j < eB[k]; ++j) a = fma(__ldcs(m2.val + j), __ldg(x2 + __ldcs(m2.idx + j)), a);
+      __stcs(T.ydir + row[k], a);
+    }
+  }
+}
+
 inline int tiled_prepare() {
   CUDA_OK(cudaFuncSetAttribute(tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmem));
+  CUDA_OK(cudaFuncSetAttribute(tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmem));
   return 0;
 }
 // kt_cat: timing category whose window the streaming kernel opens (-1: none); the epilogue functor must
@@ -323,14 +372,29 @@ template <class Epi>
 inline int tiled_launch(const TiledOp &op, const double *x1, const double *x2, Epi epi, Ctx &c, const int *skip,
                         int kt_cat = -1) {
   int launched = 1;
+  TiledDev T = op.d;
   if (op.has_tiled) {
-    tiled_kernel<0><<<op.d.ncta, kTThreads, kTSmem, c.stream>>>(op.d, x1, x2 ? x2 : x1, c.S, kt_cat, skip);
+    const bool side = T.ydir != nullptr && c.side_ready();
+    if (side) cudaEventRecord(c.ev_fork, c.stream);
+    if (op.variant == 1) tiled_kernel<1><<<T.ncta, kTThreads, kTSmem, c.stream>>>(T, x1, x2 ? x2 : x1, c.S, kt_cat, skip);
+    else tiled_kernel<0><<<T.ncta, kTThreads, kTSmem, c.stream>>>(T, x1, x2 ? x2 : x1, c.S, kt_cat, skip);
+    if (side) {  // fork: the short-row bins on the side stream, joined before the epilogue pass
+      cudaStreamWaitEvent(c.side, c.ev_fork, 0);
+      tiled_direct_kernel<0><<<c.sms * 3, kThreads, 0, c.side>>>(T, op.m1, op.m2, op.has2 ? 1 : 0, x1, x2 ? x2 : x1, skip);
+      cudaEventRecord(c.ev_join, c.side);
+      cudaStreamWaitEvent(c.stream, c.ev_join, 0);
+      ++launched;
+    } else {
+      T.ydir = nullptr;  // the epilogue pass multiplies the short rows out itself
+    }
     ++launched;
     epi.kt_cont = 1;
+  } else {
+    T.ydir = nullptr;
   }
   const long long blocks = ((long long)op.d.nrows + kThreads - 1) / kThreads;
   const int grid = (int)(blocks < c.grid_ew() ? (blocks > 0 ? blocks : 1) : c.grid_ew());
-  tiled_epilogue_kernel<Epi><<<grid, kThreads, 0, c.stream>>>(op.d, op.m1, op.m2, op.has2 ? 1 : 0, x1, x2 ? x2 : x1, epi,
+  tiled_epilogue_kernel<Epi><<<grid, kThreads, 0, c.stream>>>(T, op.m1, op.m2, op.has2 ? 1 : 0, x1, x2 ? x2 : x1, epi,
                                                               c.red, c.S, skip);
   return launched;
 }

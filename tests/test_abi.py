@@ -4,6 +4,7 @@ validation / error behaviour (no compute calls: there is no GPU in this tier).""
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -109,3 +110,23 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "scs_oracle" not in src and "oracle/" not in src.replace("oracle/_ref", ""), f
+
+
+def test_upstream_patch_adds_linear_solver_b200():
+    """integration/b200_upstream.patch applied to the reference's front end (make -C oracle ref_frontend_b200):
+    `scs.LinearSolver.B200` exists and resolves to `scs._scs_b200`, the reference's scspy.c compiled with
+    -DPY_B200 and linked against libscsb200.so (32-bit scs_int).  Runs in a subprocess: the patched package is
+    also called `scs`.  No device needed (module import and the three module functions only)."""
+    import subprocess
+    pkg = os.path.join(ROOT, "oracle", "_ref", "scs_b200")
+    if not os.path.exists(os.path.join(pkg, "scs", "__init__.py")):
+        pytest.skip("oracle/_ref/scs_b200 not built (make -C oracle ref_frontend_b200)")
+    code = ("import sys; sys.path.insert(0, %r); import scs; m = scs._SOLVER_DISPATCH[scs.LinearSolver.B200](); "
+            "import os; print(scs.LinearSolver.B200.value, os.path.basename(m.__file__).split('.')[0], m.sizeof_int(), m.sizeof_float(), m.version())" % pkg)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-1500:]
+    val, name, si, sf, ver = r.stdout.split()
+    assert val == "b200" and name == "_scs_b200" and si == "4" and sf == "8" and ver == "3.2.11"
+    patch = open(os.path.join(ROOT, "integration", "b200_upstream.patch")).read()
+    for needle in ("link_b200", "PY_B200", "PyInit__scs_b200", 'B200 = "b200"', "_scs_b200"):
+        assert needle in patch

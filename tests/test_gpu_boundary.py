@@ -1,0 +1,118 @@
+"""GPU tier (-m gpu): the drop-in boundary, driven by the REFERENCE's own code.
+
+* `scs.LinearSolver.B200`: the reference front end with integration/b200_upstream.patch applied
+  (oracle/_ref/scs_b200, `make -C oracle ref_frontend_b200`) selects `scs._scs_b200` = the reference's scspy.c
+  compiled with -DPY_B200 against libscsb200.so.
+* The reference's own pytest files (oracle/_ref/ref_tests, copied there by `make -C oracle ref_tests`) run with
+  every solve routed to that module (tests/ref_route_b200.py).
+* Level-2 plugin: the reference CORE + its C test runner (S/test/run_tests.c, 57 tests) linked against the five
+  linsys.h functions of libscsb200.so (`make -C oracle ref_ctests_b200`).
+* Two workspaces solving concurrently from two threads (scsobject.h:984-987 releases the GIL).
+All reference-built artefacts live under the git-ignored oracle/_ref and travel with gpurun; when they are
+absent the test is skipped (the build container creates them in __graft_entry__.build()).
+"""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _need(path):
+    if not os.path.exists(path):
+        pytest.skip("%s not built on this box" % os.path.relpath(path, ROOT))
+
+
+_B200_ENUM = r'''
+import sys, json
+sys.path.insert(0, %(pkg)r); sys.path.insert(0, %(root)r)
+import numpy as np, scipy.sparse as sp
+import scs
+from tests import problems
+K = dict(z=3, l=10, q=[4, 3], s=[3], ep=2)
+data, p_star = problems.gen_feasible(K, n=20, density=0.3, seed=5)
+sol = scs.SCS(data, K, linear_solver=scs.LinearSolver.B200, verbose=False, eps_abs=1e-9, eps_rel=1e-9).solve()
+ref = scs.SCS(data, K, linear_solver=scs.LinearSolver.QDLDL, verbose=False, eps_abs=1e-9, eps_rel=1e-9).solve()
+print(json.dumps(dict(solver=sol["info"]["lin_sys_solver"], status=sol["info"]["status"], pobj=sol["info"]["pobj"],
+                      ref_pobj=ref["info"]["pobj"], ref_solver=ref["info"]["lin_sys_solver"], p_star=p_star,
+                      module=scs._SOLVER_DISPATCH[scs.LinearSolver.B200]().__name__)))
+'''
+
+
+def test_linear_solver_b200_selects_the_backend(gpu, tmp_path):
+    _need(os.path.join(REF, "scs_b200", "scs", "__init__.py"))
+    import json
+    script = tmp_path / "b200_enum.py"
+    script.write_text(_B200_ENUM % dict(pkg=os.path.join(REF, "scs_b200"), root=ROOT))
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["solver"] == "sparse-indirect-b200-pcg" and out["status"] == "solved"
+    assert out["ref_solver"] != out["solver"]  # the other members of the enum still reach the reference's own backends
+    assert abs(out["pobj"] - out["ref_pobj"]) <= 1e-6 * max(1.0, abs(out["ref_pobj"]))
+    assert abs(out["pobj"] - out["p_star"]) <= 1e-5 * max(1.0, abs(out["p_star"]))
+
+
+def test_reference_pytest_files_through_b200(gpu):
+    """/root/reference/test/{test_solve_random_cone_prob, test_scs_basic, test_scs_sdp, test_scs_quad,
+    test_mix_sd_csd_cone, test_scs_object, test_scs_rand, test_warm_start_consistency}.py, unmodified."""
+    _need(os.path.join(REF, "scs_b200", "scs", "__init__.py"))
+    _need(os.path.join(REF, "ref_tests", "test_scs_basic.py"))
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(REF, "scs_b200"), os.path.join(ROOT, "tests"), env.get("PYTHONPATH", "")])
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "ref_route_b200", "-p", "no:cacheprovider",
+                        "-k", "not GPU_INDIRECT and not CPU_DENSE", os.path.join(REF, "ref_tests")],
+                       capture_output=True, text=True, timeout=1800, cwd=os.path.join(REF, "ref_tests"), env=env)
+    tail = r.stdout[-3000:] + r.stderr[-1500:]
+    assert r.returncode == 0 and " passed" in r.stdout and "routed to scs.LinearSolver.B200" in r.stdout, tail
+
+
+def test_reference_core_and_c_tests_on_the_linsys_plugin(gpu):
+    """S/test/run_tests.c + S/src/*.c (-DINDIRECT=1) with scs_init_lin_sys_work / scs_solve_lin_sys /
+    scs_update_lin_sys_diag_r / scs_free_lin_sys_work / scs_get_lin_sys_method from libscsb200.so."""
+    exe = os.path.join(REF, "run_tests_b200_linsys")
+    _need(exe)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=1800, cwd=os.path.join(REF, "ctest_data"))
+    tail = r.stdout[-2500:] + r.stderr[-1500:]
+    assert r.returncode == 0 and "ALL TESTS PASSED" in r.stdout, tail
+    assert "sparse-indirect-b200-pcg" in r.stdout, tail  # the core printed OUR plugin's name (scs.c:127)
+
+
+def test_two_threads_two_workspaces(gpu):
+    """Workspaces are independent and re-entrant across threads (SURVEY 8b "Threading"; scsobject.h:984-987):
+    two threads construct, solve and update their own problem repeatedly while the other runs; every result
+    equals the one the same problem gives when solved alone."""
+    import scs_python_b200 as scsb
+    from tests import problems
+    K = dict(z=5, l=40, q=[6, 5, 4], ep=4)
+    probs = [problems.gen_feasible(K, n=60, density=0.2, seed=s, with_P=bool(s % 2))[0] for s in (1, 2)]
+    kw = dict(verbose=False, eps_abs=1e-9, eps_rel=1e-9, max_iters=50000)
+    alone = [scsb.SCS(d, K, **kw).solve() for d in probs]
+    results, errors = [[], []], []
+
+    def work(t):
+        try:
+            for rep in range(6):
+                s = scsb.SCS(probs[t], K, **kw)
+                r = s.solve()
+                s.update(b=np.asarray(probs[t]["b"]), c=np.asarray(probs[t]["c"]))
+                r2 = s.solve(warm_start=False)
+                results[t].append((r, r2))
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+    th = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    for t in range(2):
+        assert len(results[t]) == 6
+        for r, r2 in results[t]:
+            for got in (r, r2):
+                assert got["info"]["status_val"] == 1 and got["info"]["iter"] == alone[t]["info"]["iter"]
+                assert np.array_equal(got["x"], alone[t]["x"])  # deterministic kernels: bit-identical

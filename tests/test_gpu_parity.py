@@ -196,6 +196,96 @@ def test_proj_dual_cone_vs_oracle_random(B, K):
         assert np.max(np.abs(got - ref)) <= 1e-9 * max(1.0, np.max(np.abs(ref)))
 
 
+def test_root_plus_known_answers_on_device(B):
+    """S/test/problems/test_root_plus.h:68-159 on the CUDA kernel of the ADMM loop (k_rootplus + FinRootPlus)
+    through its host-buffer hook; tolerances are the reference test's own."""
+    for c in KAT["root_plus"]["cases"]:
+        g, p_, mu, r = (np.array(c[k], float) for k in ("g", "p", "mu", "r"))
+        got = B.lib.scs_b200_root_plus(B._dptr(g), B._dptr(p_), B._dptr(mu), B._dptr(r), len(g), float(c["tau_scale"]),
+                                       float(c["eta"]))
+        assert abs(got - c["expected"]) <= 1e-10 * max(1.0, abs(c["expected"])), (len(g), got, c["expected"])
+    # a long vector: the grid reduction against numpy (different summation order: 1e-12 relative)
+    rng = np.random.RandomState(5)
+    nm = 300_001
+    g, p_, mu = rng.randn(nm), rng.randn(nm), rng.randn(nm)
+    r = np.abs(rng.randn(nm)) + 0.1
+    got = B.lib.scs_b200_root_plus(B._dptr(g), B._dptr(p_), B._dptr(mu), B._dptr(r), nm, 10.0, 0.7)
+    ref = O.root_plus(g, np.concatenate([r, [10.0]]), np.concatenate([p_, [0.0]]), np.concatenate([mu, [0.0]]), 0.7)
+    assert abs(got - ref) <= 1e-11 * max(1.0, abs(ref))
+
+
+def _psd_inputs(rng, K, kind):
+    """Packed inputs for the cones of K: random, all-negative-definite (projection = 0 for the primal cone, i.e.
+    proj_dual_cone returns the input's PSD part = 0 ... here the DUAL cone is the PSD cone itself, so a negative
+    definite input projects to 0) and rank-deficient (few non-zero eigenvalues of both signs)."""
+    parts = []
+    for s in K.get("s", []):
+        if kind == "random":
+            M = rng.randn(s, s); M = M + M.T
+        else:
+            Q, _ = np.linalg.qr(rng.randn(s, s))
+            if kind == "negdef":
+                lam = -(np.abs(rng.randn(s)) + 0.1)
+            else:  # rank deficient: 3 positive, 2 negative, the rest exactly zero
+                lam = np.zeros(s); lam[:5] = [3.0, 1.0, 0.25, -2.0, -0.5][:min(5, s)]
+            M = (Q * lam) @ Q.T
+            M = 0.5 * (M + M.T)
+        v = []
+        for j in range(s):  # lower triangle, column-major, off-diagonals * sqrt2 (cones.rst "Semidefinite cones")
+            col = M[j:, j].copy(); col[1:] *= math.sqrt(2.0)
+            v.append(col)
+        parts.append(np.concatenate(v) if v else np.zeros(0))
+    for s in K.get("cs", []):
+        if kind == "random":
+            H = rng.randn(s, s) + 1j * rng.randn(s, s); H = H + H.conj().T
+        else:
+            Q, _ = np.linalg.qr(rng.randn(s, s) + 1j * rng.randn(s, s))
+            if kind == "negdef":
+                lam = -(np.abs(rng.randn(s)) + 0.1)
+            else:
+                lam = np.zeros(s); lam[:5] = [3.0, 1.0, 0.25, -2.0, -0.5][:min(5, s)]
+            H = (Q * lam) @ Q.conj().T
+            H = 0.5 * (H + H.conj().T)
+        v = []
+        for j in range(s):  # real diagonal, then (re, im) * sqrt2 of the rows below (cones.c:1088-1095)
+            v.append([H[j, j].real])
+            below = H[j + 1:, j] * math.sqrt(2.0)
+            v.append(np.column_stack([below.real, below.imag]).ravel())
+        parts.append(np.concatenate([np.asarray(a, float).ravel() for a in v]) if v else np.zeros(0))
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("K", [dict(s=[97]), dict(s=[120]), dict(s=[200]), dict(s=[257]), dict(cs=[49]), dict(cs=[60]),
+                               dict(cs=[130]), dict(s=[225, 201]), dict(cs=[120, 101]), dict(s=[200, 40, 100], cs=[50, 7])])
+def test_psd_cluster_path_vs_oracle(B, K):
+    """PSD / complex PSD cones whose embedding dimension exceeds 96 run the 4-CTA-cluster Jacobi kernel (the path
+    BASELINE.json configs[3], s = 200, takes): projections against the oracle's LAPACK eigendecomposition
+    (cones.c:991-1148), cold and warm-started (one workspace projecting a drifting input), on random,
+    negative-definite (cones.c:1037-1041: no positive eigenvalue) and rank-deficient inputs, and on mixed sizes
+    in one launch (the shared-memory footprint is not monotone in d).  Tolerance 1e-9 relative."""
+    rng = np.random.RandomState(11)
+    m = problems.cone_len(K)
+    k, keep = B.make_cone(K)
+    w = B.lib.scs_b200_init_cone(C.byref(k), m)
+    assert w
+    try:
+        x0 = _psd_inputs(rng, K, "random")
+        dx = _psd_inputs(rng, K, "random")
+        seq = [("cold", x0)] + [("warm%d" % t, x0 + 0.02 * t * dx) for t in (1, 2, 3)]
+        seq += [("negdef", _psd_inputs(rng, K, "negdef")), ("rankdef", _psd_inputs(rng, K, "rankdef")),
+                ("back", x0 + 0.07 * dx)]
+        for name, x in seq:
+            got = np.array(x, dtype=np.float64)
+            assert B.lib.scs_b200_proj_dual_cone(B._dptr(got), w, None, None) == 0
+            ref = x.copy(); O.proj_dual_cone(ref, O.ConeWork(K, m), None, None)
+            scale = max(1.0, np.max(np.abs(x)))
+            assert np.max(np.abs(got - ref)) <= 1e-9 * scale, (name, K, float(np.max(np.abs(got - ref))))
+            if name == "negdef":
+                assert np.max(np.abs(got)) <= 1e-9 * scale
+    finally:
+        B.lib.scs_b200_finish_cone(w)
+
+
 def test_psd_projection_properties(B):
     """PSD result is PSD, idempotent and the Moreau residual is orthogonal (size-independent)."""
     rng = np.random.RandomState(2)
