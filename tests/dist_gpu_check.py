@@ -35,7 +35,11 @@ def reference_solver():
         sys.path.insert(0, p)
         try:
             import scs
-            return lambda d, K, kw: scs.SCS(d, K, verbose=False, **kw).solve(), "reference QDLDL (oracle/_ref)"
+            # QDLDL, except where its fill-in would explode (the random sparse LASSO matrix): CPU_INDIRECT there
+            def solve(d, K, kw):
+                ls = scs.LinearSolver.CPU_INDIRECT if d["A"].nnz > 300_000 else scs.LinearSolver.QDLDL
+                return scs.SCS(d, K, verbose=False, linear_solver=ls, **kw).solve()
+            return solve, "reference QDLDL / CPU_INDIRECT (oracle/_ref)"
         except Exception:
             sys.path.pop(0)
     from oracle import scs_oracle as O

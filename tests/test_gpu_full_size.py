@@ -1,0 +1,52 @@
+"""GPU tier (-m gpu): BASELINE.json-size instances against the compiled reference (tests/golden/full_ref.json,
+written by tests/golden/make_golden_full.py with the reference's QDLDL solver): configs[0] random cone QP and LP
+(n=2000, m=6000, l+q+ep cones), configs[2] SOCP portfolio (n=50k, 10k second-order cones), configs[3] MaxCut SDP
+(64 PSD cones of order 200).  north_star's correctness bar: same status, primal and dual objectives within 1e-6
+relative (at eps 1e-9), residuals meeting the run's eps (helpers.verify_solution = the reference's
+verify_solution_correct), iteration counts reported side by side."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full_ref.json")
+GOLD = json.load(open(PATH)) if os.path.exists(PATH) else {}
+
+
+def _build(name):
+    from scs_python_b200 import problems as P
+    return {"cfg1_qp": lambda: P.random_cone_qp(seed=1234, with_P=True),
+            "cfg1_lp": lambda: P.random_cone_qp(seed=1234, with_P=False),
+            "cfg3_socp": lambda: P.socp_portfolio(seed=0),
+            "cfg4_sdp": lambda: P.maxcut_sdp(seed=0)}[name]()
+
+
+def _rel(a, b):
+    return abs(a - b) / max(1.0, abs(b))
+
+
+@pytest.mark.parametrize("name", ["cfg1_qp", "cfg1_lp", "cfg3_socp", "cfg4_sdp"])
+def test_full_size_instance_vs_reference(gpu, name):
+    if name not in GOLD:
+        pytest.skip("no reference fixture for %s (tests/golden/make_golden_full.py)" % name)
+    import scs_python_b200 as scsb
+    d, K, _ = _build(name)
+    g = GOLD[name]
+    assert (g["m"], g["n"], g["nnz"]) == (d["A"].shape[0], d["A"].shape[1], d["A"].nnz)  # same instance as the fixture
+    for eps, tol in ((1e-9, 1e-6), (1e-4, 2e-3)):
+        ref = g["runs"].get("%g" % eps)
+        if ref is None:
+            continue
+        sol = scsb.SCS(d, K, verbose=False, eps_abs=eps, eps_rel=eps, max_iters=200000).solve()
+        i = sol["info"]
+        print("%s eps %g: iterations b200 %d / reference QDLDL %d, pobj %.10g / %.10g, solve %.0f ms / %.0f ms"
+              % (name, eps, i["iter"], ref["iter"], i["pobj"], ref["pobj"], i["solve_time"], ref["solve_ms"]))
+        assert i["status_val"] == ref["status_val"] == 1, (i["status"], ref["status"])
+        assert _rel(i["pobj"], ref["pobj"]) <= tol, (eps, i["pobj"], ref["pobj"])
+        assert _rel(i["dobj"], ref["dobj"]) <= tol, (eps, i["dobj"], ref["dobj"])
+        if d["A"].shape[0] <= 300_000:  # the host-side checker densifies the cone blocks; skip it for the 1.3M-row SDP
+            helpers.verify_solution(d, K, sol, eps, eps)
