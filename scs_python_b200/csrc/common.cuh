@@ -125,9 +125,23 @@ struct Ctx {
   bool own_stream = false;
   // side stream of a product that forks (tiled.cuh: the short-row pass runs in the shadow of the streaming
   // kernel); forked and joined with events, so it follows `stream` into a graph capture
-  cudaStream_t side = nullptr;
+  // One side stream per origin stream: a stream that was pulled into a capture stays in it until the capture
+  // ends, and the CG loop body is captured on a second origin stream while the main capture is still open.
+  static constexpr int kSides = 3;
+  cudaStream_t side_origin[kSides] = {nullptr, nullptr, nullptr};
+  cudaStream_t side_stream[kSides] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool side_ready() const { return side != nullptr; }
+  cudaStream_t side_for(cudaStream_t origin) {
+    for (int i = 0; i < kSides; ++i)
+      if (side_stream[i] && side_origin[i] == origin) return side_stream[i];
+    for (int i = 0; i < kSides; ++i)
+      if (!side_stream[i]) {
+        if (cudaStreamCreateWithFlags(&side_stream[i], cudaStreamNonBlocking) != cudaSuccess) { side_stream[i] = nullptr; return nullptr; }
+        side_origin[i] = origin;
+        return side_stream[i];
+      }
+    return nullptr;
+  }
   RedWs red{nullptr, nullptr, 0};
   DevScalars *S = nullptr;       // device
   DevScalars *S_host = nullptr;  // pinned mirror
@@ -154,7 +168,6 @@ struct Ctx {
     CUDA_OK(cudaMallocHost(&S_host, sizeof(DevScalars)));
     memset(S_host, 0, sizeof(DevScalars));
     CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     return 0;
@@ -168,8 +181,11 @@ struct Ctx {
     if (ev) cudaEventDestroy(ev);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
-    if (side) cudaStreamDestroy(side);
-    side = nullptr; ev_fork = ev_join = nullptr;
+    for (int i = 0; i < kSides; ++i) {
+      if (side_stream[i]) cudaStreamDestroy(side_stream[i]);
+      side_stream[i] = nullptr; side_origin[i] = nullptr;
+    }
+    ev_fork = ev_join = nullptr;
     if (own_stream && stream) cudaStreamDestroy(stream);
     red = RedWs{nullptr, nullptr, 0};
     S = nullptr; S_host = nullptr; ev = nullptr; stream = nullptr;

@@ -430,8 +430,8 @@ int TiledOp::build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force) {
       }
     }
     {
-      const char *e = getenv("SCS_B200_TILED_U");  // groups per register buffer of the streaming kernel: 8 or 12
-      variant = (e && atoi(e) == 12) ? 1 : 0;
+      const char *e = getenv("SCS_B200_TILED_U");  // groups per register buffer of the streaming kernel: 8 or 6
+      variant = (e && atoi(e) == 6) ? 1 : 0;      // (12 was measured 15 % slower: 122 registers, profiles/r2c_*)
     }
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) break;
     lap("plan+upload");

@@ -147,7 +147,7 @@ __device__ __forceinline__ unsigned atom_add_acq_rel(unsigned *p, unsigned v) {
 
 // Streaming kernel: partial sums of every work item into its scratch slot.  kt_cat >= 0: this launch
 // opens the in-region timing window of that SpMV category (common.cuh kt_begin).
-// kVariant: groups of 32 entries a warp keeps in flight = 2 x U with U = 8 (variant 0) or 12 (variant 1)
+// kVariant: groups of 32 entries a warp keeps in flight = 2 x U with U = 8 (variant 0) or 6 (variant 1)
 template <int kVariant>
 __global__ void __launch_bounds__(kTThreads, 1)
 tiled_kernel(TiledDev T, const double *__restrict__ x1, const double *x2, DevScalars *S, int kt_cat,
@@ -200,7 +200,7 @@ tiled_kernel(TiledDev T, const double *__restrict__ x1, const double *x2, DevSca
       }
     }
   };
-  constexpr int U = kVariant == 0 ? 8 : 12;
+  constexpr int U = kVariant == 0 ? 8 : 6;
   for (int ii = i0; ii < i1; ++ii) {
     const TItem im = T.items[ii];
     const unsigned long long t_item = threadIdx.x == 0 ? gtimer() : 0ull;
@@ -374,14 +374,15 @@ inline int tiled_launch(const TiledOp &op, const double *x1, const double *x2, E
   int launched = 1;
   TiledDev T = op.d;
   if (op.has_tiled) {
-    const bool side = T.ydir != nullptr && c.side_ready();
+    cudaStream_t sd = T.ydir != nullptr ? c.side_for(c.stream) : nullptr;
+    const bool side = sd != nullptr;
     if (side) cudaEventRecord(c.ev_fork, c.stream);
     if (op.variant == 1) tiled_kernel<1><<<T.ncta, kTThreads, kTSmem, c.stream>>>(T, x1, x2 ? x2 : x1, c.S, kt_cat, skip);
     else tiled_kernel<0><<<T.ncta, kTThreads, kTSmem, c.stream>>>(T, x1, x2 ? x2 : x1, c.S, kt_cat, skip);
     if (side) {  // fork: the short-row bins on the side stream, joined before the epilogue pass
-      cudaStreamWaitEvent(c.side, c.ev_fork, 0);
-      tiled_direct_kernel<0><<<c.sms * 3, kThreads, 0, c.side>>>(T, op.m1, op.m2, op.has2 ? 1 : 0, x1, x2 ? x2 : x1, skip);
-      cudaEventRecord(c.ev_join, c.side);
+      cudaStreamWaitEvent(sd, c.ev_fork, 0);
+      tiled_direct_kernel<0><<<c.sms * 3, kThreads, 0, sd>>>(T, op.m1, op.m2, op.has2 ? 1 : 0, x1, x2 ? x2 : x1, skip);
+      cudaEventRecord(c.ev_join, sd);
       cudaStreamWaitEvent(c.stream, c.ev_join, 0);
       ++launched;
     } else {

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--combos", default="")
     a = ap.parse_args()
     data, cone = bench.workload(a.scale, seed=0)
-    combos = list(itertools.product(("0", "1"), ("0", "1"), ("8", "12")))
+    combos = list(itertools.product(("0", "1"), ("0", "1"), ("8", "6")))
     if a.combos:
         combos = [tuple(c.split(",")) for c in a.combos.split(";")]
     ref_obj = None
