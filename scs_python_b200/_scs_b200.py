@@ -25,7 +25,8 @@ import warnings
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libscsb200.so")
+# SCS_B200_LIBPATH: a development build of the same library (tools/spmv_variants.py compares tile geometries)
+_LIB_PATH = os.environ.get("SCS_B200_LIBPATH") or os.path.join(_HERE, "libscsb200.so")
 if not os.path.exists(_LIB_PATH):
     raise ImportError(
         "scs_python_b200: %s not found. Build it with `python -m scs_python_b200.build` "

@@ -41,6 +41,30 @@ def needs_build() -> bool:
     return any(_newer(d, LIB) for d in deps)
 
 
+def build_alt(cfg: int = 1) -> str:
+    """Development build of the alternative tile geometry of the tiled SpMV engine (csrc/tiled.cuh,
+    -DB200_TILED_CFG) into libscsb200_cfg<k>.so; loaded with SCS_B200_LIBPATH by tools/spmv_variants.py."""
+    nvcc = _nvcc()
+    out = os.path.join(HERE, "libscsb200_cfg%d.so" % cfg)
+    objdir = os.path.join(HERE, "build", "cfg%d" % cfg)
+    os.makedirs(objdir, exist_ok=True)
+
+    def one(src):
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        r = subprocess.run([nvcc, *NVCC_FLAGS, "-DB200_TILED_CFG=%d" % cfg, "-c", os.path.join(CSRC, src), "-o", o],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        return o
+    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(one, SOURCES))
+    r = subprocess.run([nvcc, "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker",
+                        "-Bsymbolic", "-lcudart", "-ldl"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return out
+
+
 def build(force: bool = False, verbose: bool = True) -> str:
     if not force and not needs_build():
         return LIB
@@ -77,4 +101,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    if "--alt" in sys.argv:
+        print(build_alt(1))
+    else:
+        build(force="--force" in sys.argv)

@@ -419,8 +419,11 @@ int TiledOp::build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force) {
         const bool empty = p1[(size_t)r1] == p1[(size_t)r0] && (!m2 || p2[(size_t)r1] == p2[(size_t)r0]);
         if (h_binfo[(size_t)rb].y == 0 && !empty) db.push_back(rb);
       }
-      const char *e = getenv("SCS_B200_TILED_SIDE");  // "0": the epilogue pass multiplies the short rows out itself
-      const bool side_on = !(e && atoi(e) == 0);
+      // "1": multiply the short rows out on a side stream in the shadow of the streaming kernel.  Off by default:
+      // measured on the bench workload it does not pay (0.436 -> 0.440 ms per product, profiles/r2c_spmv_variants.txt);
+      // the streaming kernel is latency-bound and the extra traffic slows it by as much as the epilogue pass gains
+      const char *e = getenv("SCS_B200_TILED_SIDE");
+      const bool side_on = e && atoi(e) == 1;
       d.ndbins = 0;
       if (side_on && nitems > 0 && !db.empty()) {
         if (dev_alloc(&d.dbins, db.size()) || dev_alloc_zero(&d.ydir, (size_t)nrows, st) ||

@@ -41,14 +41,35 @@
 
 namespace b200 {
 
+// Tile geometry (compile time, -DB200_TILED_CFG=k):
+//   0: 16384 rows x 4096 columns, 16 warps (1024 rows each), 3 x-slice stages of 32 KB, 2 x 8 groups in flight
+//      per warp  -- round 1
+//   1: 8192 rows x 8192 columns, 32 warps (256 rows each), 2 x-slice stages of 64 KB, 2 x 4 groups in flight per
+//      warp.  Same tile area (same x-slice traffic per non-zero), same (warp, column bin) segment size (same
+//      padding), same bytes in flight per SM, but twice the warps: the per-group chain (shared-memory load ->
+//      DFMA -> store, ~45 % of the stall cycles in profiles/r2d_tiled_stream_ncu.txt) is hidden behind eight
+//      warps per scheduler instead of four.
+#ifndef B200_TILED_CFG
+#define B200_TILED_CFG 0
+#endif
+#if B200_TILED_CFG == 1
+constexpr int kTR = 8192;              // rows per row bin
+constexpr int kTC = 8192;              // columns per column bin
+constexpr int kTW = 32;                // warps per CTA
+constexpr int kTStages = 2;            // x-slice stages
+constexpr int kTU0 = 4, kTU1 = 3;      // groups per register buffer of the two streaming-kernel variants
+#else
 constexpr int kTR = 16384;             // rows per row bin
 constexpr int kTC = 4096;              // columns per column bin
 constexpr int kTW = 16;                // warps per CTA
-constexpr int kTThreads = kTW * 32;
 constexpr int kTStages = 3;            // x-slice stages
+constexpr int kTU0 = 8, kTU1 = 6;
+#endif
+constexpr int kTThreads = kTW * 32;
 constexpr int kTRW = kTR / kTW;        // rows one warp owns inside a row bin
-constexpr unsigned kTFlag = 1u << 12;  // set in the first group of a (warp, column bin) segment
-constexpr int kTRowShift = 13;         // packed entry: local row << 13 | flag << 12 | local column
+constexpr unsigned kTFlag = 1u << 13;  // set in the first group of a (warp, column bin) segment
+constexpr int kTRowShift = 14;         // packed entry: local row << 14 | flag << 13 | local column (<= 8192 columns,
+                                       // <= 16384 + 32 accumulators incl. the lanes' dummies: 15 + 1 + 13 bits)
 constexpr size_t kTSmem = (size_t)(kTR + 32) * 8 + (size_t)kTStages * kTC * 8 + 64;
 
 // one work item: a row bin restricted to a contiguous range of its active column bins
@@ -200,7 +221,7 @@ tiled_kernel(TiledDev T, const double *__restrict__ x1, const double *x2, DevSca
       }
     }
   };
-  constexpr int U = kVariant == 0 ? 8 : 6;
+  constexpr int U = kVariant == 0 ? kTU0 : kTU1;
   for (int ii = i0; ii < i1; ++ii) {
     const TItem im = T.items[ii];
     const unsigned long long t_item = threadIdx.x == 0 ? gtimer() : 0ull;

@@ -14,5 +14,5 @@ _mod = _b200()
 assert _mod.__name__.endswith("_scs_b200") or _mod.sizeof_int() == 4
 
 
-def pytest_report_header(config):
-    return "reference tests routed to scs.LinearSolver.B200 (%s, %s)" % (_mod.__file__, _mod.version())
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    terminalreporter.write_line("reference tests routed to scs.LinearSolver.B200 (%s, %s)" % (_mod.__file__, _mod.version()))

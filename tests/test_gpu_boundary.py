@@ -102,7 +102,12 @@ def test_two_threads_two_workspaces(gpu):
     K = dict(z=5, l=40, q=[6, 5, 4], ep=4)
     probs = [problems.gen_feasible(K, n=60, density=0.2, seed=s, with_P=bool(s % 2))[0] for s in (1, 2)]
     kw = dict(verbose=False, eps_abs=1e-9, eps_rel=1e-9, max_iters=50000)
-    alone = [scsb.SCS(d, K, **kw).solve() for d in probs]
+    def pair(d):  # what one workspace returns for solve, update(b, c), solve (the second solve starts from the
+        s = scsb.SCS(d, K, **kw)  # scale the first one adapted to, as in the reference: scs.c:1112-1189)
+        r = s.solve()
+        s.update(b=np.asarray(d["b"]), c=np.asarray(d["c"]))
+        return r, s.solve(warm_start=False)
+    alone = [pair(d) for d in probs]
     results, errors = [[], []], []
 
     def work(t):
@@ -121,7 +126,7 @@ def test_two_threads_two_workspaces(gpu):
     assert not errors, errors
     for t in range(2):
         assert len(results[t]) == 6
-        for r, r2 in results[t]:
-            for got in (r, r2):
-                assert got["info"]["status_val"] == 1 and got["info"]["iter"] == alone[t]["info"]["iter"]
-                assert np.array_equal(got["x"], alone[t]["x"])  # deterministic kernels: bit-identical
+        for pair_t in results[t]:
+            for got, ref in zip(pair_t, alone[t]):
+                assert got["info"]["status_val"] == 1 and got["info"]["iter"] == ref["info"]["iter"]
+                assert np.array_equal(got["x"], ref["x"])  # deterministic kernels: bit-identical

@@ -37,7 +37,8 @@ def test_full_size_instance_vs_reference(gpu, name):
     d, K, _ = _build(name)
     g = GOLD[name]
     assert (g["m"], g["n"], g["nnz"]) == (d["A"].shape[0], d["A"].shape[1], d["A"].nnz)  # same instance as the fixture
-    for eps, tol in ((1e-9, 1e-6), (1e-4, 2e-3)):
+    # (eps of the run, relative tolerance on the objectives): two correct solvers agree to about the stopping tolerance
+    for eps, tol in ((1e-9, 1e-6), (1e-6, 2e-5), (1e-4, 2e-3)):
         ref = g["runs"].get("%g" % eps)
         if ref is None:
             continue
