@@ -274,6 +274,10 @@ double scs_b200_bench_spmv(ScsWork *w, scs_int which, scs_int reps, double *alg_
  * count (0 when the operator runs on the row engine). */
 scs_int scs_b200_tiled_profile(ScsWork *w, scs_int which, double *out, scs_int cap);
 
+/* Tile geometry of the tiled SpMV engine in this build: {rows per row bin, columns per column bin, warps per
+ * CTA, x-slice stages} (csrc/tiled.cuh). */
+void scs_b200_tiled_geometry(scs_int out[4]);
+
 /* Host-only test hook: the work plan of the tiled SpMV engine for a synthetic cell map (no device needed).
  * hg[rb * ncb + cb] = groups of the (row bin, column bin) cell, p1 / p2 = row pointers (p2 may be NULL).
  * items_out: 5 ints per item {cta, row bin, slot, first index into seq_out, one past the last};

@@ -181,6 +181,8 @@ lib.scs_b200_csv_header.argtypes = []
 lib.scs_b200_tiled_plan.restype = c_int
 lib.scs_b200_tiled_plan.argtypes = [c_int, c_int, p_int, p_int, p_int, c_int, p_int, c_int, p_int, c_int, p_int, p_double,
                                     p_int, p_int]
+lib.scs_b200_tiled_geometry.restype = None
+lib.scs_b200_tiled_geometry.argtypes = [C.POINTER(c_int * 4)]
 lib.scs_b200_tiled_profile.restype = c_int
 lib.scs_b200_tiled_profile.argtypes = [C.c_void_p, c_int, p_double, c_int]
 lib.scs_b200_solve_batch.restype = c_int

@@ -41,7 +41,7 @@ def needs_build() -> bool:
     return any(_newer(d, LIB) for d in deps)
 
 
-def build_alt(cfg: int = 1) -> str:
+def build_alt(cfg: int = 0) -> str:
     """Development build of the alternative tile geometry of the tiled SpMV engine (csrc/tiled.cuh,
     -DB200_TILED_CFG) into libscsb200_cfg<k>.so; loaded with SCS_B200_LIBPATH by tools/spmv_variants.py."""
     nvcc = _nvcc()
@@ -102,6 +102,6 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
 if __name__ == "__main__":
     if "--alt" in sys.argv:
-        print(build_alt(1))
+        print(build_alt(0))
     else:
         build(force="--force" in sys.argv)

@@ -544,9 +544,17 @@ __device__ __forceinline__ void jacobi_angle(double a, double b, double g, doubl
   sn = cs * t;
 }
 
+// A sweep in which every rotated pair was already orthogonal to kPsdSmallCos (|cos| of the angle between the two
+// columns) is the last one: one-sided Jacobi converges quadratically, so after those rotations the largest
+// cosine is of the order kPsdSmallCos^2 * d ~ 1e-12 relative to the column norms -- below what the projection
+// needs (tests: 1e-9 against LAPACK) -- and the sweep that would only verify it (a third to a half of the cost of
+// a rotating sweep: all the dot products, no rotation) is not run.
+constexpr double kPsdSmallCos2 = 1e-14;  // (1e-7)^2
+
 // One column pair of the one-sided Jacobi iteration on shared-memory columns: rotate
-// (g_p, g_q) and (v_p, v_q) so that g_p . g_q = 0.  Returns true when a rotation was applied.
-__device__ __forceinline__ bool jacobi_pair_smem(double *gp, double *gq, double *vp, double *vq, int d, int lane,
+// (g_p, g_q) and (v_p, v_q) so that g_p . g_q = 0.  Returns 0: no rotation, 1: rotated a pair that was
+// orthogonal to kPsdSmallCos, 2: rotated a pair that was not.
+__device__ __forceinline__ int jacobi_pair_smem(double *gp, double *gq, double *vp, double *vq, int d, int lane,
                                                  double tol2) {
   double a = 0.0, b = 0.0, g = 0.0;
   for (int i = lane; i < d; i += 32) {
@@ -559,7 +567,8 @@ __device__ __forceinline__ bool jacobi_pair_smem(double *gp, double *gq, double 
     b += __shfl_xor_sync(0xffffffffu, b, o);
     g += __shfl_xor_sync(0xffffffffu, g, o);
   }
-  if (!(g * g > tol2 * (a * b))) return false;  // |g| <= tol sqrt(a b): already orthogonal (also NaN / g == 0)
+  if (!(g * g > tol2 * (a * b))) return 0;  // |g| <= tol sqrt(a b): already orthogonal (also NaN / g == 0)
+  const int level = (g * g > kPsdSmallCos2 * (a * b)) ? 2 : 1;
   // tan of the rotation angle: t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b - a) / (2 g),
   // written with one sqrt, one division and one rsqrt
   double cs, sn;
@@ -572,7 +581,7 @@ __device__ __forceinline__ bool jacobi_pair_smem(double *gp, double *gq, double 
     vp[i] = cs * vu - sn * vw;
     vq[i] = sn * vu + cs * vw;
   }
-  return true;
+  return level;
 }
 
 // round `rnd` of the round-robin tournament over `cnt` (even) players: the k-th pairing
@@ -642,7 +651,7 @@ k_psd_jacobi(const PsdEntry *__restrict__ ents, PsdState *__restrict__ state, in
         }
         __syncthreads();
         const int nbb = nloc - na;
-        bool rot = false;
+        int rot = 0;  // 0 / 1 / 2, see jacobi_pair_smem
         if (rb == 0) {
           // pairs inside each of the two blocks, once per sweep (every block appears exactly once in
           // a block round): two independent tournaments side by side
@@ -657,7 +666,7 @@ k_psd_jacobi(const PsdEntry *__restrict__ ents, PsdState *__restrict__ state, in
               if (rnd >= cnt - 1 || p >= cap || q >= cap) continue;
               if (p > q) { const int t = p; p = q; q = t; }
               p += base; q += base;
-              rot |= jacobi_pair_smem(Gs + (size_t)p * d, Gs + (size_t)q * d, Vs + (size_t)p * d, Vs + (size_t)q * d, d, lane, tol2);
+              rot = max(rot, jacobi_pair_smem(Gs + (size_t)p * d, Gs + (size_t)q * d, Vs + (size_t)p * d, Vs + (size_t)q * d, d, lane, tol2));
             }
             __syncthreads();
           }
@@ -700,6 +709,7 @@ k_psd_jacobi(const PsdEntry *__restrict__ ents, PsdState *__restrict__ state, in
                   g += __shfl_xor_sync(0xffffffffu, g, o);
                 }
                 if (g * g > tol2 * (a * b)) {
+                  rot = max(rot, (g * g > kPsdSmallCos2 * (a * b)) ? 2 : 1);
                   double cs, sn;
                   jacobi_angle(a, b, g, cs, sn);
                   double a_new = 0.0;
@@ -717,7 +727,6 @@ k_psd_jacobi(const PsdEntry *__restrict__ ents, PsdState *__restrict__ state, in
                     }
                   }
                   a = warp_sum(a_new);
-                  rot = true;
                 }
               }
               __syncthreads();
@@ -739,13 +748,13 @@ k_psd_jacobi(const PsdEntry *__restrict__ ents, PsdState *__restrict__ state, in
             for (int k = wid; k < nmax; k += nw) {
               const int p = k, q = (k + rnd) % nmax;
               if (p >= na || q >= nbb) continue;
-              rot |= jacobi_pair_smem(Gs + (size_t)p * d, Gs + (size_t)(na + q) * d, Vs + (size_t)p * d,
-                                      Vs + (size_t)(na + q) * d, d, lane, tol2);
+              rot = max(rot, jacobi_pair_smem(Gs + (size_t)p * d, Gs + (size_t)(na + q) * d, Vs + (size_t)p * d,
+                                              Vs + (size_t)(na + q) * d, d, lane, tol2));
             }
             __syncthreads();
           }
         }
-        if (rot && lane == 0) sh_rot = 1;
+        if (rot && lane == 0) atomicMax(&sh_rot, rot);
         for (int idx = tid; idx < nloc * d; idx += nthr) {
           const int c = idx / d, i = idx - c * d;
           const long long dst = (long long)(c < na ? a0 + c : b0 + (c - na)) * d + i;
@@ -759,10 +768,10 @@ k_psd_jacobi(const PsdEntry *__restrict__ ents, PsdState *__restrict__ state, in
     int rotated = sh_rot;
     if (C > 1) {
       cg::cluster_group cl = cg::this_cluster();
-      for (int r = 0; r < C; ++r) rotated |= *cl.map_shared_rank(&sh_rot, r);
+      for (int r = 0; r < C; ++r) rotated = max(rotated, *cl.map_shared_rank(&sh_rot, r));
     }
     sync_all();  // everyone has read the flags before they are cleared
-    if (!rotated) break;
+    if (rotated < 2) break;  // no rotation at all, or only pairs that were already orthogonal to kPsdSmallCos
   }
   if (tid == 0 && rank == 0) state[cone].sweeps = sweep + 1;
 }

@@ -295,6 +295,12 @@ extern "C" scs_int scs_b200_tiled_plan(scs_int nrows, scs_int ncb, const scs_int
   return nitems;
 }
 
+// tile geometry of this build (csrc/tiled.cuh, -DB200_TILED_CFG): rows per row bin, columns per column bin,
+// warps per CTA, x-slice stages
+extern "C" void scs_b200_tiled_geometry(scs_int out[4]) {
+  out[0] = kTR; out[1] = kTC; out[2] = kTW; out[3] = kTStages;
+}
+
 void TiledOp::destroy() {
   dev_free(d.items); dev_free(d.cta_off); dev_free(d.seq); dev_free(d.cta_seq_off); dev_free(d.gbase);
   dev_free(d.pk); dev_free(d.val); dev_free(d.partial); dev_free(d.binfo); dev_free(d.prof);
@@ -435,6 +441,8 @@ int TiledOp::build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force) {
     {
       const char *e = getenv("SCS_B200_TILED_U");  // groups per register buffer of the streaming kernel: 8 or 6
       variant = (e && atoi(e) == 6) ? 1 : 0;      // (12 was measured 15 % slower: 122 registers, profiles/r2c_*)
+      const char *e2 = getenv("SCS_B200_TILED_EB");
+      epi_eb = (e2 && atoi(e2) == 8) ? 8 : 4;
     }
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) break;
     lap("plan+upload");

@@ -49,8 +49,11 @@ namespace b200 {
 //      padding), same bytes in flight per SM, but twice the warps: the per-group chain (shared-memory load ->
 //      DFMA -> store, ~45 % of the stall cycles in profiles/r2d_tiled_stream_ncu.txt) is hidden behind eight
 //      warps per scheduler instead of four.
+// Measured on the bench workload (profiles/r2e_spmv_tile*.txt): Gp product 0.437 ms (cfg 0) -> 0.389 ms (cfg 1),
+// A p 0.406 -> 0.366 ms, although cfg 1 stages twice the x-slice bytes (8 kTC per cell): the kernel is bound by
+// latency, not by L2 -> SM bytes.  cfg 1 is the default; -DB200_TILED_CFG=0 rebuilds the round-1 geometry.
 #ifndef B200_TILED_CFG
-#define B200_TILED_CFG 0
+#define B200_TILED_CFG 1
 #endif
 #if B200_TILED_CFG == 1
 constexpr int kTR = 8192;              // rows per row bin
@@ -110,6 +113,7 @@ struct TiledOp {
   std::vector<int> cta_items;
   bool has_tiled = false;  // false: every row bin is a short-row bin (the epilogue pass does it all)
   int variant = 0;         // streaming-kernel variant (tiled_kernel<variant>: groups in flight per warp)
+  int epi_eb = 4;          // rows per thread in flight in the epilogue pass (4 or 8)
   CsrDev m1, m2;
   bool has2 = false;
   // Build from CSR(M1) [and CSR(M2) with the same row count, acting on a second vector]:
@@ -289,14 +293,13 @@ tiled_kernel(TiledDev T, const double *__restrict__ x1, const double *x2, DevSca
 // Epilogue pass (high occupancy): y_r = sum of the pieces of r's row bin in piece order, or -- for a
 // short-row bin -- the row's product straight from the CSR arrays (one thread per row: these rows hold a
 // couple of entries); then q = epi.load(r) ; epi.apply(st, r, y_r, q) ; finally epi.finish as in row_kernel.
-template <class Epi>
+template <class Epi, int EB>
 __global__ void __launch_bounds__(kThreads)
 tiled_epilogue_kernel(TiledDev T, CsrDev m1, CsrDev m2, int has2, const double *__restrict__ x1,
                       const double *x2, Epi epi, RedWs ws, DevScalars *S, const int *skip) {
   if (skip != nullptr && *skip != 0) return;
   typename Epi::State st;
   epi.init(st);
-  constexpr int EB = 4;
   const int stride = gridDim.x * blockDim.x;
   for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < T.nrows; base += stride * EB) {
     typename Epi::Pre pre[EB];
@@ -416,8 +419,12 @@ inline int tiled_launch(const TiledOp &op, const double *x1, const double *x2, E
   }
   const long long blocks = ((long long)op.d.nrows + kThreads - 1) / kThreads;
   const int grid = (int)(blocks < c.grid_ew() ? (blocks > 0 ? blocks : 1) : c.grid_ew());
-  tiled_epilogue_kernel<Epi><<<grid, kThreads, 0, c.stream>>>(T, op.m1, op.m2, op.has2 ? 1 : 0, x1, x2 ? x2 : x1, epi,
-                                                              c.red, c.S, skip);
+  if (op.epi_eb == 8)
+    tiled_epilogue_kernel<Epi, 8><<<grid, kThreads, 0, c.stream>>>(T, op.m1, op.m2, op.has2 ? 1 : 0, x1, x2 ? x2 : x1, epi,
+                                                                   c.red, c.S, skip);
+  else
+    tiled_epilogue_kernel<Epi, 4><<<grid, kThreads, 0, c.stream>>>(T, op.m1, op.m2, op.has2 ? 1 : 0, x1, x2 ? x2 : x1, epi,
+                                                                   c.red, c.S, skip);
   return launched;
 }
 inline bool tiled_aligned(const double *x) { return (reinterpret_cast<uintptr_t>(x) & 15u) == 0; }

@@ -227,7 +227,15 @@ def test_solve_batch_wrapper_fills_the_c_structures(monkeypatch):
 
 
 # ------------------------------------------------------------ tiled SpMV engine: the host plan ------
-TR, TC = 16384, 4096   # csrc/tiled.cuh: rows per row bin, columns per column bin
+def _tile_geometry():
+    import ctypes as C
+    from scs_python_b200 import _scs_b200 as B
+    g = (B.c_int * 4)()
+    B.lib.scs_b200_tiled_geometry(C.byref(g))
+    return int(g[0]), int(g[1])
+
+
+TR, TC = _tile_geometry()   # csrc/tiled.cuh: rows per row bin, columns per column bin of this build
 
 
 def _tiled_plan(nrows, hg, p1, p2, sms):
