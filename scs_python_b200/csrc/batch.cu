@@ -37,12 +37,12 @@ int current_device();
 namespace {
 
 typedef unsigned short u16;
-constexpr int kBT = 128;            // threads per CTA
+constexpr int kBT = 256;            // threads per CTA
 constexpr int kBW = kBT / 32;       // warps per CTA
 constexpr int kBAaMax = 10;         // lookback handled in-CTA
 constexpr int kBC = 2 * kBAaMax + 1;  // columns of the AA elimination [A | Y | g]
 constexpr int kBRed = 24;           // reduction outputs per call (>= kBC)
-constexpr int kBCtasPerSm = 3;
+constexpr int kBCtasPerSm = 2;
 
 // glbopts.h constants
 constexpr int kFeasIters = 1, kRescaleMinIters = 100, kConvInterval = 25;
@@ -71,14 +71,14 @@ struct BOut {
 
 // shared-memory carve-up, identical on host and device (offsets in doubles / u16 elements)
 struct BLay {
-  int Aval, Pval, u, ut, v, vp, rsk, g, dr, b, c, D, E, cp, cr, cGp, cM, tmp, ws, red, aaR, aaScr, Ginv, nd;
+  int Aval, AvalR, Pval, u, ut, v, vp, rsk, g, dr, b, c, D, E, cp, cr, cGp, cM, tmp, ws, red, aaR, aaScr, Ginv, nd;
   int st_bytes;
   int Arow, Aperm, Acol, Acp, Arp, Pcol, Prp, qoff, qlen, ni;
   __host__ __device__ explicit BLay(const BDims &d) {
     const int l = d.n + d.m + 1;
     int o = 0;
     auto take = [&o](int cnt) { int r = o; o += cnt; return r; };
-    Aval = take(d.nnzA); Pval = take(d.nnzP);
+    Aval = take(d.nnzA); AvalR = take(d.nnzA); Pval = take(d.nnzP);  // AvalR: the values once more, in CSR order
     u = take(l); ut = take(l); v = take(l); vp = take(d.mem > 0 ? l : 0); rsk = take(l); g = take(l);
     dr = take(l); b = take(d.m); c = take(d.n); D = take(d.m); E = take(d.n);
     cp = take(d.n); cr = take(d.n); cGp = take(d.n); cM = take(d.n); tmp = take(d.m); ws = take(d.n);
@@ -167,9 +167,9 @@ struct Resid {  // ScsResiduals scalars in the ORIGINAL scaling (scs_work.h:29-5
 
 struct B {  // one CTA's view of its problem
   int n, m, l, nnzA, nnzP, z, nl, nq, tid;
-  double *Aval, *Pval, *u, *ut, *v, *vp, *rsk, *g, *dr, *b, *c, *D, *E, *cp, *cr, *cGp, *cM, *tmp, *ws;
+  double *Aval, *AvalR, *Pval, *u, *ut, *v, *vp, *rsk, *g, *dr, *b, *c, *D, *E, *cp, *cr, *cGp, *cM, *tmp, *ws;
   double *aaR, *aaScr, *Ginv;
-  int direct, refine, gld;
+  int direct, refine, gld, gparts, gshift;
   u16 *Arow, *Aperm, *Acol, *Acp, *Arp, *Pcol, *Prp, *qoff, *qlen;
   AaState *st;
   // AA global workspace
@@ -183,7 +183,7 @@ struct B {  // one CTA's view of its problem
 
 __device__ __forceinline__ double rowdot_A(const B &s, int i, const double *x) {  // (A x)_i, CSR view
   double acc = 0.0;
-  for (int k = s.Arp[i]; k < s.Arp[i + 1]; ++k) acc = fma(s.Aval[s.Aperm[k]], x[s.Acol[k]], acc);
+  for (int k = s.Arp[i]; k < s.Arp[i + 1]; ++k) acc = fma(s.AvalR[k], x[s.Acol[k]], acc);  // (valid after equilibrate())
   return acc;
 }
 __device__ __forceinline__ double coldot_A(const B &s, int j, const double *y) {  // (A' y)_j, CSC as given
@@ -266,43 +266,58 @@ __device__ void build_ginv(B &s) {
     for (int k = s.Acp[j]; k < s.Acp[j + 1]; ++k) {
       const int i = s.Arow[k];
       const double a = s.Aval[k] / s.dr[n + i];
-      for (int kk = s.Arp[i]; kk < s.Arp[i + 1]; ++kk) col[s.Acol[kk]] = fma(a, s.Aval[s.Aperm[kk]], col[s.Acol[kk]]);
+      for (int kk = s.Arp[i]; kk < s.Arp[i + 1]; ++kk) col[s.Acol[kk]] = fma(a, s.AvalR[kk], col[s.Acol[kk]]);
     }
     for (int k = s.Prp[j]; k < s.Prp[j + 1]; ++k) col[s.Pcol[k]] += s.Pval[k];
     col[j] += s.dr[j];
   }
   __syncthreads();
-  double *f = s.cGp;  // column k before the step
+  // Gauss-Jordan, one elimination step per k.  Thread (j, part) owns the rows [r0, r1) of column j (kBT / n
+  // parts per column), so the rank-one update is a stride-1 walk down a column of the odd-ld array: no
+  // integer division, no bank conflicts, two barriers per step.
+  double *f = s.cGp;   // column k before the step
+  double *rowk = s.cr;  // row k before the step, scaled by the pivot
+  const int parts = kBT / n > 0 ? kBT / n : 1;
+  const int rows_pp = (n + parts - 1) / parts;
   for (int k = 0; k < n; ++k) {
     const double p = 1.0 / G[k + (size_t)k * ld];
-    BFOR(i, n) f[i] = G[i + (size_t)k * ld];
-    __syncthreads();
-    BFOR(j, n) if (j != k) G[k + (size_t)j * ld] *= p;  // row k
-    __syncthreads();
-    for (int e = s.tid; e < n * n; e += kBT) {
-      const int i = e % n, j = e / n;
-      if (i == k) continue;
-      double *g = G + i + (size_t)j * ld;
-      *g = (j == k) ? -f[i] * p : fma(-f[i], G[k + (size_t)j * ld], *g);
+    BFOR(i, n) { f[i] = G[i + (size_t)k * ld]; rowk[i] = G[k + (size_t)i * ld] * p; }
+    __syncthreads();  // column k and row k are saved (and the pivot read) before anything below overwrites them
+    for (int t = s.tid; t < n * parts; t += kBT) {
+      const int j = t % n, part = t / n;  // (one division per step, not per element)
+      const int r0 = part * rows_pp, r1 = r0 + rows_pp < n ? r0 + rows_pp : n;
+      double *col = G + (size_t)j * ld;
+      if (j != k) {
+        const double gkj = rowk[j];
+        for (int i = r0; i < r1; ++i) col[i] = (i == k) ? gkj : fma(-f[i], gkj, col[i]);
+      } else {
+        for (int i = r0; i < r1; ++i) col[i] = (i == k) ? p : -f[i] * p;
+      }
     }
-    if (s.tid == 0) G[k + (size_t)k * ld] = p;
     __syncthreads();
   }
 }
 
-// out_j = sum_k Ginv[k, j] rhs_k  (Ginv symmetric: column j read, stride 1 down the column)
+// out_j = sum_k Ginv[k, j] rhs_k  (Ginv symmetric: column j read down the column).  `parts` (a power of two,
+// <= kBT / n) adjacent lanes share one output: lane h of the group sums the terms k = h, h + parts, ... and the
+// group adds its partial sums with a butterfly -- a fixed order, and kBT / n times shorter dependent chains.
 __device__ __forceinline__ void ginv_apply(const B &s, const double *rhs, double *out, bool accumulate) {
-  BFOR(j, s.n) {
-    const double *col = s.Ginv + (size_t)j * s.gld;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int k = 0;
-    for (; k + 3 < s.n; k += 4) {
-      a0 = fma(col[k], rhs[k], a0); a1 = fma(col[k + 1], rhs[k + 1], a1);
-      a2 = fma(col[k + 2], rhs[k + 2], a2); a3 = fma(col[k + 3], rhs[k + 3], a3);
+  const int n = s.n, parts = s.gparts, sh = s.gshift;
+  const int total = ((n << sh) + 31) & ~31;  // whole warps: the butterfly needs every lane
+  for (int t = s.tid; t < total; t += kBT) {
+    const int j = t >> sh, h = t & (parts - 1);
+    const bool valid = j < n;
+    const double *col = s.Ginv + (size_t)(valid ? j : 0) * s.gld;
+    double a0 = 0.0, a1 = 0.0;
+    int k = h;
+    for (; k + parts < n; k += 2 * parts) {
+      a0 = fma(col[k], rhs[k], a0);
+      a1 = fma(col[k + parts], rhs[k + parts], a1);
     }
-    for (; k < s.n; ++k) a0 = fma(col[k], rhs[k], a0);
-    const double r = (a0 + a1) + (a2 + a3);
-    out[j] = accumulate ? out[j] + r : r;
+    if (k < n) a0 = fma(col[k], rhs[k], a0);
+    double r = a0 + a1;
+    for (int o = parts >> 1; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if (valid && h == 0) out[j] = accumulate ? out[j] + r : r;
   }
 }
 
@@ -682,7 +697,7 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
   double *sd = reinterpret_cast<double *>(smem_raw);
   B s;
   s.tid = threadIdx.x;
-  s.Aval = sd + L.Aval; s.Pval = sd + L.Pval; s.u = sd + L.u; s.ut = sd + L.ut; s.v = sd + L.v; s.vp = sd + L.vp;
+  s.Aval = sd + L.Aval; s.AvalR = sd + L.AvalR; s.Pval = sd + L.Pval; s.u = sd + L.u; s.ut = sd + L.ut; s.v = sd + L.v; s.vp = sd + L.vp;
   s.rsk = sd + L.rsk; s.g = sd + L.g; s.dr = sd + L.dr; s.b = sd + L.b; s.c = sd + L.c; s.D = sd + L.D; s.E = sd + L.E;
   s.cp = sd + L.cp; s.cr = sd + L.cr; s.cGp = sd + L.cGp; s.cM = sd + L.cM; s.tmp = sd + L.tmp; s.ws = sd + L.ws;
   s.red.buf = sd + L.red; s.red.phase = 0;
@@ -705,6 +720,9 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
     const BProb pb = a.probs[pid];
     s.n = pb.n; s.m = pb.m; s.l = pb.n + pb.m + 1; s.nnzA = pb.nnzA; s.nnzP = pb.nnzP;
     s.z = pb.z; s.nl = pb.l; s.nq = pb.nq; s.cg_its = 0; s.gld = pb.n | 1;
+    s.gshift = 0;
+    while (s.gshift < 5 && (pb.n << (s.gshift + 1)) <= kBT) ++s.gshift;  // lanes per output of ginv_apply
+    s.gparts = 1 << s.gshift;
     const int n = s.n, m = s.m, l = s.l;
     const int mem = g.aa_mem < l ? g.aa_mem : l;  // aa_init, aa.c:657-700
     const bool aa_on = mem > 0;
@@ -748,6 +766,10 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
     const long long ck_begin = clock64();
     if (g.normalize) {
       { const long long c0 = clock64(); equilibrate(s); ck[0] += clock64() - c0; }
+    }
+    BFOR(k, s.nnzA) s.AvalR[k] = s.Aval[s.Aperm[k]];  // final values in CSR order (one indirection less per non-zero)
+    __syncthreads();
+    if (g.normalize) {
       double mx[1] = {0.0};
       BFOR(i, m) { const double bi = s.b[i] * s.D[i]; s.b[i] = bi; mx[0] = fmax(mx[0], fabs(bi)); }
       BFOR(j, n) { const double cj = s.c[j] * s.E[j]; s.c[j] = cj; mx[0] = fmax(mx[0], fabs(cj)); }
