@@ -580,6 +580,9 @@ struct SCS_WORK {
   int n = 0, m = 0, l = 0;
   // the graph-launched front half of one ADMM iteration (k_prep .. cones), CG loop = WHILE node
   bool use_graph = false;
+  int cg_unroll = 3;          // CG iterations captured as plain kernel nodes in front of the WHILE node
+  bool cg_unroll_auto = true; // follow the observed CG iterations per ADMM iteration (re-capture at residual checks)
+  long long unroll_cg0 = 0; int unroll_it0 = 0;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   cudaStream_t st_body = nullptr;
@@ -1061,6 +1064,7 @@ static int update_scale(SCS_WORK *w, int iter) {
     w->sum_log_scale_factor = 0;
     w->n_log_scale_factor = 0;
     w->last_scale_update_iter = iter;
+    w->unroll_cg0 = -1;  // the g solve below must not count as CG iterations of an ADMM iteration
     w->stgs.scale = new_scale;
     if (set_diag_r(w)) return -1;
     if (w->ls.update_precond()) return -1;
@@ -1169,6 +1173,10 @@ static int build_iter_graph(SCS_WORK *w) {
   const char *env = getenv("SCS_B200_NO_GRAPH");
   if (env && env[0] == '1') return 0;
   if (w->dist) return 0;  // NCCL all-reduces sit inside the CG loop: stream launches, host-read stop flag
+  if (const char *eu = getenv("SCS_B200_CG_UNROLL")) {  // fixed number of unrolled CG iterations (tests, comparisons)
+    w->cg_unroll = std::max(0, std::min(32, atoi(eu)));
+    w->cg_unroll_auto = false;
+  }
   cudaStream_t st = c.stream;
   const long long l0 = c.launches, s0 = c.spmv_calls;
   bool capturing = false, ok = false;
@@ -1181,6 +1189,15 @@ static int build_iter_graph(SCS_WORK *w) {
     if (cudaStreamBeginCaptureToGraph(st, w->graph, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess) break;
     capturing = true;
     if (enqueue_front_head(w, loop)) break;
+    // The first cg_unroll CG iterations are plain kernel nodes (kernels launched after convergence return at
+    // once); only what is left goes through the WHILE node.  A conditional-node trip costs ~25 us on B200
+    // (profiles/r2e_configs_all_arms.jsonl: 10.8 us per lin-sys kernel against 5.3 us per cone kernel on the
+    // n = 2000 cone QP), which dominated problems that need two or three CG iterations per ADMM iteration.
+    {
+      bool bad = false;
+      for (int k = 0; k < w->cg_unroll && !bad; ++k) bad = w->ls.enqueue_cg_iter(w->u_t, loop, -1) != 0;
+      if (bad) break;
+    }
     // WHILE node after everything captured so far
     cudaStreamCaptureStatus status;
     const cudaGraphNode_t *deps = nullptr;
@@ -1227,6 +1244,15 @@ static int build_iter_graph(SCS_WORK *w) {
   }
   w->use_graph = true;
   return 0;
+}
+
+// re-capture with the current w->cg_unroll (the stream is idle: called right after a residual check)
+static int rebuild_iter_graph(SCS_WORK *w) {
+  if (w->gexec) { cudaGraphExecDestroy(w->gexec); w->gexec = nullptr; }
+  if (w->graph) { cudaGraphDestroy(w->graph); w->graph = nullptr; }
+  if (w->st_body) { cudaStreamDestroy(w->st_body); w->st_body = nullptr; }
+  w->use_graph = false;
+  return build_iter_graph(w);
 }
 
 static void free_work(SCS_WORK *w) {
@@ -1698,6 +1724,7 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
   // ---- update_work: reset_tracking + warm/cold start + g (scs.c:1079-1105)
   w->last_scale_update_iter = 0; w->sum_log_scale_factor = 0.; w->n_log_scale_factor = 0; w->scale_updates = 0;
   w->time_limit_reached = 0;
+  w->unroll_cg0 = -1; w->unroll_it0 = 0;
   w->r_n.last_iter = -1; w->r_o.last_iter = -1;
   cudaMemsetAsync(&c.S->aa_rejected, 0, 2 * sizeof(int), st);  // safeguard counters of this solve
   if (warm_start) {
@@ -1769,6 +1796,19 @@ extern "C" scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_in
       if (check && g_int_detected && !w->dist) return failure(w, m_out, n_out, sol, info, SCS_SIGINT, "interrupted", "interrupted");
       if (populate_residuals(w, i)) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error in residuals", "failure");
       w->n_checks++;
+      if (w->use_graph && w->cg_unroll_auto && (w->unroll_cg0 < 0 || i <= w->unroll_it0)) {
+        w->unroll_cg0 = c.S_host->cg_its_total; w->unroll_it0 = i;  // baseline (start of a solve, after a scale update)
+      } else if (w->use_graph && w->cg_unroll_auto) {
+        // follow the CG iteration count: enough unrolled nodes for the typical ADMM iteration, no more
+        const double kavg = (double)(c.S_host->cg_its_total - w->unroll_cg0) / (double)(i - w->unroll_it0);
+        int want = (int)ceil(kavg + 0.25);
+        want = want < 1 ? 1 : (want > 24 ? 24 : want);
+        w->unroll_cg0 = c.S_host->cg_its_total; w->unroll_it0 = i;
+        if (want != w->cg_unroll) {
+          w->cg_unroll = want;
+          if (rebuild_iter_graph(w)) return failure(w, m_out, n_out, sol, info, SCS_FAILED, "error re-capturing the iteration graph", "failure");
+        }
+      }
       if (check) {
         if ((info->status_val = has_converged(w)) != 0) break;
         if (stgs->time_limit_secs && ms_since(t0) > 1000. * stgs->time_limit_secs) {
