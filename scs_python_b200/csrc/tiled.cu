@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <cstring>
 #include <queue>
 #include <vector>
 
@@ -97,22 +98,81 @@ __global__ void __launch_bounds__(kThreads) k_tl_pad(unsigned *__restrict__ pk, 
   }
 }
 
+// Where every entry of a segment goes: dstpos[p] = group * 32 + lane inside the segment's slot range.
+//
+// A 64-bit shared-memory access is served one half-warp at a time, and the kernel touches shared memory three
+// times per entry: it reads x_s[col], reads y_s[row] and writes y_s[row].  Two lanes of a half-warp collide when
+// their rows (or columns) fall into the same bank pair, i.e. agree modulo 16.  So a group of 32 slots is two
+// half-slots of 16 lanes, and the entries of a segment are dealt greedily, in the order of the sort (bank pair of
+// the row, then row-major), into the half-slot where they collide least: a row collision costs two extra
+// wavefronts (load + store), a column collision one.  Entries of one row are consecutive in that order and must
+// land in different GROUPS (the update of a group is one unordered read-modify-write): a bit mask of the groups
+// the current row already uses enforces it.  If the greedy pass runs out of feasible half-slots (nearly full
+// segments), or the segment has more than 32 groups, the segment falls back to the plain dealing (entry k ->
+// group k mod G, chunk k div G, chunks alternating between the half-warps), which is feasible by construction.
+// One thread per segment; a segment holds a few hundred entries.
+__global__ void __launch_bounds__(128)
+k_tl_deal(const unsigned *__restrict__ sval, long long nnz1, const int *__restrict__ sstart, const int *__restrict__ gbase,
+          long long nseg, const int *__restrict__ rowof, CsrDev M1, CsrDev M2, int *__restrict__ dstpos, int greedy) {
+  for (long long seg = blockIdx.x * (long long)blockDim.x + threadIdx.x; seg < nseg; seg += (long long)gridDim.x * blockDim.x) {
+    const int s0 = sstart[seg], cnt = sstart[seg + 1] - s0;
+    if (cnt <= 0) continue;
+    const int G = gbase[seg + 1] - gbase[seg];
+    bool ok = greedy && G <= 32;
+    if (ok) {
+      unsigned short rmask[64], cmask[64];
+      unsigned char fill[64];
+      const int nh = 2 * G;
+      for (int h = 0; h < nh; ++h) { rmask[h] = 0; cmask[h] = 0; fill[h] = 0; }
+      int prev_row = -1;
+      unsigned used = 0u;
+      for (int k = 0; k < cnt && ok; ++k) {
+        const unsigned src = sval[s0 + k];
+        const int row = rowof[src];
+        const int col = (long long)src < nnz1 ? M1.idx[src] : M2.idx[src - nnz1];
+        const int rc = row & 15, cc = col & 15;
+        if (row != prev_row) { used = 0u; prev_row = row; }
+        int best = -1, bc = 99;
+        int h = k % nh;
+        for (int t = 0; t < nh; ++t, h = (h + 1 == nh) ? 0 : h + 1) {
+          if (fill[h] >= 16 || ((used >> (h >> 1)) & 1u)) continue;
+          const int c = (((rmask[h] >> rc) & 1) << 1) + ((cmask[h] >> cc) & 1);
+          if (c < bc) { bc = c; best = h; if (c == 0) break; }
+        }
+        if (best < 0) { ok = false; break; }
+        dstpos[s0 + k] = (best >> 1) * 32 + (best & 1) * 16 + fill[best];
+        rmask[best] |= (unsigned short)(1u << rc);
+        cmask[best] |= (unsigned short)(1u << cc);
+        fill[best]++;
+        used |= 1u << (best >> 1);
+      }
+    }
+    if (!ok) {
+      for (int k = 0; k < cnt; ++k) {
+        const int grp = k % G, chunk = k / G;
+        dstpos[s0 + k] = grp * 32 + (((chunk & 1) << 4) | (chunk >> 1));
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_tl_scatter(const unsigned *__restrict__ skey, const unsigned *__restrict__ sval, long long total, long long nnz1,
              const int *__restrict__ sstart, const int *__restrict__ gbase, const int *__restrict__ rowof, CsrDev M1,
-             CsrDev M2, unsigned *__restrict__ pk, double *__restrict__ val, int lane_perm) {
+             CsrDev M2, unsigned *__restrict__ pk, double *__restrict__ val, const int *__restrict__ dstpos) {
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
     const unsigned seg = skey[p] >> 4;
     const unsigned src = sval[p];
     const int k = (int)(p - sstart[seg]);
-    const int g0 = gbase[seg], G = gbase[seg + 1] - g0;
-    // entry k of the segment (sorted by accumulator bank pair, then row-major) goes to group k mod G; the
-    // chunk k div G picks the lane.  Consecutive chunks hold the same or neighbouring bank pairs, and a
-    // 64-bit shared-memory access is served one half-warp at a time, so consecutive chunks alternate between
-    // the two half-warps: inside a half-warp the lanes of a group are then two chunks (~2G sorted entries, more
-    // than one bank-pair class) apart.
-    const int grp = k % G, chunk = k / G;
-    const int lane = lane_perm ? (((chunk & 1) << 4) | (chunk >> 1)) : chunk;
+    const int g0 = gbase[seg];
+    int grp, lane;
+    if (dstpos) {  // dealt by k_tl_deal
+      const int d = dstpos[p];
+      grp = d >> 5; lane = d & 31;
+    } else {       // round-1 dealing: entry k -> group k mod G, lane k div G
+      const int G = gbase[seg + 1] - g0;
+      grp = k % G; lane = k / G;
+    }
     int col;
     double v;
     if ((long long)src < nnz1) { col = M1.idx[src]; v = M1.val[src]; }
@@ -379,9 +439,20 @@ int TiledOp::build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force) {
     k_tl_iota<<<grid, kThreads, 0, st>>>(sv, total);
     if (cub::DeviceRadixSort::SortPairs(tmp, tb3, key, key2, sv, sv2, (int)total, 0, bits, st) != cudaSuccess) break;
     k_tl_pad<<<grid, kThreads, 0, st>>>(d.pk, d.val, slots);
-    const char *lp_env = getenv("SCS_B200_TILED_LANE_PERM");  // "0": the round-1 dealing (comparison runs)
+    // SCS_B200_TILED_DEAL: "greedy" (default) / "perm" (plain dealing, half-warp-aware lanes) / "r1" (round-1 dealing)
+    const char *deal_env = getenv("SCS_B200_TILED_DEAL");
+    const int deal = (deal_env && !strcmp(deal_env, "r1")) ? 0 : ((deal_env && !strcmp(deal_env, "perm")) ? 1 : 2);
+    int *dstpos = nullptr;
+    if (deal > 0) {
+      if (dev_alloc(&dstpos, (size_t)total)) break;
+      const long long blocks = (nseg + 127) / 128;
+      k_tl_deal<<<(unsigned)std::min<long long>(blocks, 1 << 20), 128, 0, st>>>(sv2, nnz1, sstart, d.gbase, nseg, rowof, m1,
+                                                                                m2 ? *m2 : m1, dstpos, deal == 2 ? 1 : 0);
+      c.launches++;
+    }
     k_tl_scatter<<<grid, kThreads, 0, st>>>(key2, sv2, total, nnz1, sstart, d.gbase, rowof, m1, m2 ? *m2 : m1, d.pk, d.val,
-                                            (lp_env && atoi(lp_env) == 0) ? 0 : 1);
+                                            dstpos);
+    if (dstpos) { cudaStreamSynchronize(st); dev_free(dstpos); }
     k_tl_flag_empty<<<grid, kThreads, 0, st>>>(cnt, d.gbase, nseg, d.pk);
     c.launches += 4;
     lap("sort+scatter");

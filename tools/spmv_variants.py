@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Tiled SpMV engine variants on the bench workload, one process, one data set:
-lane dealing (SCS_B200_TILED_LANE_PERM), side-stream short-row pass (SCS_B200_TILED_SIDE), groups in flight
-per warp (SCS_B200_TILED_U).  Prints ms per product (CUDA events, back-to-back launches) and the algorithmic
+entry dealing (SCS_B200_TILED_DEAL = greedy / perm / r1), side-stream short-row pass (SCS_B200_TILED_SIDE), groups
+in flight per warp (SCS_B200_TILED_U).  Prints ms per product (CUDA events, back-to-back launches) and the algorithmic
 TB/s of both CG products for every combination.
 
     python tools/spmv_variants.py [--scale 1.0] [--reps 30]
@@ -25,12 +25,12 @@ def main():
     ap.add_argument("--combos", default="")
     a = ap.parse_args()
     data, cone = bench.workload(a.scale, seed=0)
-    combos = list(itertools.product(("0", "1"), ("0", "1"), ("8", "6")))
+    combos = list(itertools.product(("greedy", "perm"), ("0",), ("8",)))
     if a.combos:
         combos = [tuple(c.split(",")) for c in a.combos.split(";")]
     ref_obj = None
     for perm, side, u in combos:
-        os.environ.update(SCS_B200_TILED_LANE_PERM=perm, SCS_B200_TILED_SIDE=side, SCS_B200_TILED_U=u)
+        os.environ.update(SCS_B200_TILED_DEAL=perm, SCS_B200_TILED_SIDE=side, SCS_B200_TILED_U=u)
         s = scsb.SCS(data, cone, verbose=False, max_iters=50, eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0)
         inner = s._solver
         a_ms, a_b = inner.bench_spmv(0, a.reps)
@@ -39,7 +39,7 @@ def main():
         obj = r["info"]["pobj"]
         if ref_obj is None:
             ref_obj = obj
-        print(json.dumps(dict(lane_perm=perm, side=side, U=u, a_ms=a_ms, g_ms=g_ms, a_tbs=a_b / a_ms / 1e9, g_tbs=g_b / g_ms / 1e9,
+        print(json.dumps(dict(deal=perm, side=side, U=u, a_ms=a_ms, g_ms=g_ms, a_tbs=a_b / a_ms / 1e9, g_tbs=g_b / g_ms / 1e9,
                               g_frac_of_6553=g_b / g_ms / 1e9 / 6.5536, pobj_50its=obj,
                               pobj_rel_diff=abs(obj - ref_obj) / max(1.0, abs(ref_obj)))), flush=True)
         inner.finish()
