@@ -162,7 +162,7 @@ int chunks_build(Ctx &c, ChunkList &out, const CsrDev &a, const CsrDev *b) {
   }
   CUDA_OK(cudaStreamSynchronize(c.stream));
   std::vector<int4> ch;
-  build_chunks_host(a.nrows, pa.data(), b ? pb.data() : nullptr, ch);
+  build_chunks_host(a.nrows, pa.data(), b ? pb.data() : nullptr, ch, c.sms);
   out.n = (int)ch.size();
   if (dev_alloc(&out.d, ch.size())) return -1;
   CUDA_OK(cudaMemcpyAsync(out.d, ch.data(), sizeof(int4) * ch.size(), cudaMemcpyHostToDevice, c.stream));

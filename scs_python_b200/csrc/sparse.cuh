@@ -38,9 +38,15 @@ struct ChunkList {
 // Build the chunk list on the host from one or two row-pointer arrays (second may be null;
 // used to fuse P's rows with A' rows).  Greedy: close a chunk when it holds >= target nnz,
 // >= max_rows rows, or the row-length class changes by more than 2x.
-inline void build_chunks_host(int nrows, const int *ptr1, const int *ptr2, std::vector<int4> &out) {
-  const long long target = 4096;
-  const int max_rows = 2048;
+// sms: SM count of the device.  A matrix with few non-zeros is cut into smaller chunks so that the kernel still
+// spreads over the whole device: with 4096-entry chunks the n = 2000 cone QP of BASELINE.json configs[0] (60 k
+// non-zeros) ran on 15 CTAs and every SpMV launch took ~10 us of serial dependent loads
+// (profiles/r2g_configs_unroll*.jsonl); chunk size = total / (4 x SMs), clamped to [512, 4096].
+inline void build_chunks_host(int nrows, const int *ptr1, const int *ptr2, std::vector<int4> &out, int sms = 148) {
+  long long total_nnz = (long long)ptr1[nrows] + (ptr2 ? (long long)ptr2[nrows] : 0);
+  long long target = total_nnz / (4ll * (sms > 0 ? sms : 148));
+  target = target < 512 ? 512 : (target > 4096 ? 4096 : target);
+  const int max_rows = target >= 4096 ? 2048 : 256;
   const long long long_row = 16384;
   out.clear();
   int r = 0;
