@@ -580,8 +580,12 @@ struct SCS_WORK {
   int n = 0, m = 0, l = 0;
   // the graph-launched front half of one ADMM iteration (k_prep .. cones), CG loop = WHILE node
   bool use_graph = false;
-  int cg_unroll = 3;          // CG iterations captured as plain kernel nodes in front of the WHILE node
-  bool cg_unroll_auto = true; // follow the observed CG iterations per ADMM iteration (re-capture at residual checks)
+  // CG iterations captured as plain kernel nodes in front of the WHILE node, and whether that number follows the
+  // observed CG iterations per ADMM iteration (re-capture at residual checks).  Off by default: measured on
+  // Cfg-1 / Cfg-3 the conditional node costs nothing that unrolling saves (profiles/r2g_configs_unroll*.jsonl), and the
+  // re-captures cost ~30 ms on the cone LP.  SCS_B200_CG_UNROLL=k fixes k; SCS_B200_CG_UNROLL=auto turns following on.
+  int cg_unroll = 0;
+  bool cg_unroll_auto = false;
   long long unroll_cg0 = 0; int unroll_it0 = 0;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
@@ -1173,9 +1177,9 @@ static int build_iter_graph(SCS_WORK *w) {
   const char *env = getenv("SCS_B200_NO_GRAPH");
   if (env && env[0] == '1') return 0;
   if (w->dist) return 0;  // NCCL all-reduces sit inside the CG loop: stream launches, host-read stop flag
-  if (const char *eu = getenv("SCS_B200_CG_UNROLL")) {  // fixed number of unrolled CG iterations (tests, comparisons)
-    w->cg_unroll = std::max(0, std::min(32, atoi(eu)));
-    w->cg_unroll_auto = false;
+  if (const char *eu = getenv("SCS_B200_CG_UNROLL")) {  // unrolled CG iterations (tests, comparisons)
+    if (!strcmp(eu, "auto")) { if (!w->cg_unroll_auto) { w->cg_unroll_auto = true; w->cg_unroll = 3; } }
+    else { w->cg_unroll = std::max(0, std::min(32, atoi(eu))); w->cg_unroll_auto = false; }
   }
   cudaStream_t st = c.stream;
   const long long l0 = c.launches, s0 = c.spmv_calls;
@@ -1189,10 +1193,9 @@ static int build_iter_graph(SCS_WORK *w) {
     if (cudaStreamBeginCaptureToGraph(st, w->graph, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess) break;
     capturing = true;
     if (enqueue_front_head(w, loop)) break;
-    // The first cg_unroll CG iterations are plain kernel nodes (kernels launched after convergence return at
-    // once); only what is left goes through the WHILE node.  A conditional-node trip costs ~25 us on B200
-    // (profiles/r2e_configs_all_arms.jsonl: 10.8 us per lin-sys kernel against 5.3 us per cone kernel on the
-    // n = 2000 cone QP), which dominated problems that need two or three CG iterations per ADMM iteration.
+    // Optionally the first cg_unroll CG iterations are plain kernel nodes (kernels launched after convergence return
+    // at once) and only what is left goes through the WHILE node: an experiment that showed the conditional node is
+    // not what makes small problems slow (see SCS_WORK::cg_unroll).
     {
       bool bad = false;
       for (int k = 0; k < w->cg_unroll && !bad; ++k) bad = w->ls.enqueue_cg_iter(w->u_t, loop, -1) != 0;

@@ -83,14 +83,19 @@ def test_reference_pytest_files_through_b200(gpu):
 
 
 def test_reference_core_and_c_tests_on_the_linsys_plugin(gpu):
-    """S/test/run_tests.c + S/src/*.c (-DINDIRECT=1) with scs_init_lin_sys_work / scs_solve_lin_sys /
-    scs_update_lin_sys_diag_r / scs_free_lin_sys_work / scs_get_lin_sys_method from libscsb200.so."""
-    exe = os.path.join(REF, "run_tests_b200_linsys")
+    """The reference CORE (S/src/*.c, -DINDIRECT=1) and the reference's own C test cases with scs_init_lin_sys_work /
+    scs_solve_lin_sys / scs_update_lin_sys_diag_r / scs_free_lin_sys_work / scs_get_lin_sys_method from libscsb200.so.
+    Default: oracle/ctests_quick_main.c, 30 of the cases of S/test/run_tests.c (about a minute: every lin-sys call
+    crosses PCIe in this mode).  SCS_B200_LONG_TESTS=1: S/test/run_tests.c itself, all 57 (about nine minutes; passed
+    on B200, profiles/r2d_pytest_new.txt)."""
+    long_run = os.environ.get("SCS_B200_LONG_TESTS") == "1"
+    exe = os.path.join(REF, "run_tests_b200_linsys" if long_run else "run_tests_b200_linsys_quick")
     _need(exe)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=1800, cwd=os.path.join(REF, "ctest_data"))
     tail = r.stdout[-2500:] + r.stderr[-1500:]
     assert r.returncode == 0 and "ALL TESTS PASSED" in r.stdout, tail
     assert "sparse-indirect-b200-pcg" in r.stdout, tail  # the core printed OUR plugin's name (scs.c:127)
+    assert ("Tests run: 57" if long_run else "Tests run: 30") in r.stdout, tail
 
 
 def test_two_threads_two_workspaces(gpu):
