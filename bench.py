@@ -80,8 +80,8 @@ def config_of(data, cone, scale, ips, n_gpus):
                 l2_policy="inputs_exceed_l2 (A+A' = %.2f GB >> 126 MB L2)" % (2 * 12e-9 * data["A"].nnz),
                 iters_per_step=ips,
                 parallelism=("single GPU" if n_gpus == 1 else
-                             "one problem, A row-partitioned over %d GPUs (NCCL all-reduce of the shared block of "
-                             "A_g'z_g per CG iteration)" % n_gpus))
+                             "one problem, A row-partitioned over %d GPUs (all-reduce of the shared block of "
+                             "A_g'z_g per CG iteration over NVLink peer memory / NCCL)" % n_gpus))
 
 
 class ClockSampler(threading.Thread):
@@ -496,9 +496,11 @@ def run_b200(args):
             dst = st1
             out["collectives"] = dict(per_rank_calls_in_long_call=int(dst["collectives"] - st0["collectives"]),
                                       per_rank_bytes_in_long_call=int(dst["collective_bytes"] - st0["collective_bytes"]),
-                                      note="NCCL all-reduces issued by rank 0 during update + solve of the long call: one of "
+                                      note="collectives issued by rank 0 during update + solve of the long call: one sum of "
                                            "(shared block + p'Gp) and one scalar gather per CG iteration, scalar gathers per "
-                                           "ADMM iteration, Anderson-acceleration trapezoids every 10th")
+                                           "ADMM iteration, Anderson-acceleration trapezoids every 10th.  The two of the CG "
+                                           "loop are kernels over CUDA-IPC-mapped peer memory (NVLink) when the ranks can map "
+                                           "each other (SCS_B200_DIST_P2P=0: NCCL), the rest are ncclAllReduce")
     solver._solver.finish()
     del solver
 

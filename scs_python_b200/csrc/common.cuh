@@ -114,6 +114,20 @@ enum ResIdx {
   R_COUNT
 };
 
+// Peer-memory exchange of the row-partitioned mode (dist.cuh): every rank maps the other ranks' all-reduce vector
+// and a small block of flags / scalar slots (CUDA IPC over NVLink / NVSwitch); the collectives of the CG loop are
+// then plain kernels that read and write peer memory.
+struct PeerSync {
+  unsigned flag_in[kMaxWorld], flag_out[kMaxWorld], flag_sc[kMaxWorld];
+  unsigned epoch_ar, epoch_sc, done_cnt, pad;
+  double grecv[2][kMaxWorld * kMaxRedVals];  // scalar slots, double-buffered by epoch parity
+};
+struct PeerPtrs {
+  double *vec[kMaxWorld];     // base of the all-reduce vector region of every rank ([rank] = local)
+  PeerSync *sync[kMaxWorld];
+  int world, rank;
+};
+
 struct Ctx {
   int device = 0;
   int sms = 148;
@@ -121,6 +135,10 @@ struct Ctx {
   int rank = 0, world = 1;
   int n_sh = 0;    // shared (replicated) columns: the prefix [0, n_sh) of every local n-vector
   int cnt_lo = 0;  // reductions over n-space count [cnt_lo, n): 0 on rank 0, n_sh on the others
+  bool p2p = false;        // peer-memory collectives set up (dist.cu: dist_p2p_setup); else NCCL
+  PeerPtrs peers{};
+  void *p2p_arena = nullptr;                 // local allocation holding [PeerSync | vector region]
+  void *p2p_opened[2 * kMaxWorld] = {};      // IPC mappings to close
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   // side stream of a product that forks (tiled.cuh: the short-row pass runs in the shadow of the streaming

@@ -401,8 +401,17 @@ int LinSys::init(Ctx *ctx, const ScsMatrix *Ah, const ScsMatrix *Ph) {
   }
   // Gp carries kGpFront doubles in front of it: Gp[-1] is the scalar p'Gp of a row-partitioned solve,
   // all-reduced in one call with the shared block Gp[0, n_sh) (Gp[-2] pads the region to 16 bytes)
+  // Row-partitioned mode: that region lives in an arena the other ranks map (CUDA IPC) so that the all-reduce is a
+  // kernel over peer memory (dist.cu: dist_p2p_setup); when mapping is not possible it is an ordinary allocation
+  // and the exchange goes through NCCL.
+  if (c->dist) {
+    double *vec = nullptr;
+    if (dist_p2p_setup(*c, (size_t)n + kGpFront, &vec)) return -1;
+    if (c->p2p) { Gp_base = vec; Gp_in_arena = true; }
+  }
   if (dev_alloc_zero(&M, (size_t)n, c->stream) || dev_alloc_zero(&p, (size_t)n, c->stream) ||
-      dev_alloc_zero(&r, (size_t)n, c->stream) || dev_alloc_zero(&Gp_base, (size_t)n + kGpFront, c->stream) ||
+      dev_alloc_zero(&r, (size_t)n, c->stream) ||
+      (!Gp_in_arena && dev_alloc_zero(&Gp_base, (size_t)n + kGpFront, c->stream)) ||
       dev_alloc_zero(&z, (size_t)n, c->stream) || dev_alloc_zero(&tmp, (size_t)m, c->stream))
     return -1;
   Gp = Gp_base + kGpFront;
@@ -436,7 +445,9 @@ void LinSys::destroy() {
   if (own_diag_r) dev_free(diag_r);
   diag_r = nullptr;
   dev_free(Pdiag);
-  dev_free(M); dev_free(p); dev_free(r); dev_free(Gp_base); dev_free(z); dev_free(tmp); dev_free(pp);
+  dev_free(M); dev_free(p); dev_free(r); dev_free(z); dev_free(tmp); dev_free(pp);
+  if (Gp_in_arena) { dist_p2p_teardown(*c); Gp_base = nullptr; Gp_in_arena = false; }
+  else dev_free(Gp_base);
   Gp = nullptr;
 }
 
@@ -499,6 +510,13 @@ int LinSys::dist_At(const double *zin, double *out, const int *skip, bool with_s
   else
     row_kernel<ElemMul, ElemMul, EpiStoreT, false>
         <<<chAt.grid, kThreads, 0, c->stream>>>(At, ea, At, ea, chAt.d, chAt.n, es, c->red, c->S, skip);
+  return dist_reduce_gp(out, with_scalar, skip);
+}
+
+// sum over the ranks, in place, of the shared block of `out` (== Gp) [and the two scalars in front of it]
+int LinSys::dist_reduce_gp(double *out, bool with_scalar, const int *skip) {
+  if (c->p2p && out == Gp)
+    return dist_p2p_allreduce(*c, with_scalar ? kGpFront - 2 : kGpFront, (long long)c->n_sh + (with_scalar ? 2 : 0), skip);
   if (with_scalar) return dist_allreduce(*c, out - 2, (size_t)c->n_sh + 2, 0);
   return dist_allreduce(*c, out, (size_t)c->n_sh, 0);
 }

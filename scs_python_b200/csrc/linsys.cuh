@@ -40,6 +40,7 @@ struct LinSys {
   double *M = nullptr, *p = nullptr, *r = nullptr, *Gp = nullptr, *z = nullptr;  // n
   static constexpr int kGpFront = 8;  // doubles allocated in front of Gp (Gp[-1]: all-reduced scalar, dist mode)
   double *Gp_base = nullptr;
+  bool Gp_in_arena = false;  // Gp_base lives in the peer-mapped arena of the row-partitioned mode (dist.cu)
   double *pp = nullptr;  // n, row-partitioned mode only: P p + R_x p
   double *tmp = nullptr;                                                          // m
   long long tot_cg_its = 0;
@@ -74,6 +75,7 @@ struct LinSys {
   // row-partitioned mode (dist.cuh)
   int launch_A_scaled_dot(const double *x, double *out, const int *skip);
   int dist_At(const double *zin, double *out, const int *skip, bool with_scalar, int kt_cat);
+  int dist_reduce_gp(double *out, bool with_scalar, const int *skip);
   // launchers shared with the ADMM driver
   int launch_A_scaled(const double *x, double *out, const int *skip, int tag = -1, bool counted = true);  // out = R_y^-1 A x
   int launch_G(const double *zin, const double *pin, double *out, const int *skip, int tag = -1,

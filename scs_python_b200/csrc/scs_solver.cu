@@ -917,7 +917,7 @@ static int populate_residuals(SCS_WORK *w, int iter) {
       EpiStore es; es.y = ls.Gp;
       row_kernel<ElemMul, ElemMul, EpiStore, false>
           <<<ls.chAt.grid, kThreads, 0, c.stream>>>(ls.At, ea, ls.At, ea, ls.chAt.d, ls.chAt.n, es, c.red, c.S, nullptr);
-      if (dist_allreduce(c, ls.Gp, (size_t)c.n_sh, 0)) return -1;
+      if (ls.dist_reduce_gp(ls.Gp, false, nullptr)) return -1;
       epi.extra = ls.Gp;
       epi.cnt_lo = c.cnt_lo;
       row_kernel<ElemMul, ElemMul, EpiResAt, false>
