@@ -309,9 +309,10 @@ scs_int scs_b200_get_marks(const ScsWork *w, ScsB200Marks *out);
  * scs_init.  Workspaces created afterwards take the FULL problem on every rank, keep a
  * cone-aligned block of rows of A and the columns those rows touch (columns touched by one rank only
  * are private to it, the others are replicated), and return the full (x, y, s).  Collectives per CG
- * iteration: one NCCL sum all-reduce of the shared block of A_g' z_g with the scalar p'Gp riding along, and
- * one gather of two reduction scalars; a few scalar gathers per ADMM iteration; Anderson acceleration
- * gathers one (mem x (2 mem + 1)) trapezoid per rank.  world == 1 with SCS_B200_DIST_SELFTEST=1 in the
+ * iteration: one sum all-reduce of the shared block of A_g' z_g with the scalar p'Gp riding along, and
+ * one gather of two reduction scalars -- both kernels over CUDA-IPC-mapped peer memory when the ranks can map each
+ * other (SCS_B200_DIST_P2P=0: ncclAllReduce); a few scalar gathers per ADMM iteration; Anderson acceleration
+ * gathers one (mem x (2 mem + 1)) trapezoid per rank (NCCL).  world == 1 with SCS_B200_DIST_SELFTEST=1 in the
  * environment runs the same code path on one GPU (collectives degenerate to copies). */
 scs_int scs_b200_dist_unique_id(void *out128);
 scs_int scs_b200_dist_init(scs_int rank, scs_int world, const void *id128);
