@@ -213,10 +213,10 @@ def reference_factory():
     scs, kind = import_reference()
     if scs is not None:
         class _R:
-            def __init__(self, data, cone, k):
+            def __init__(self, data, cone, k, time_limit=0.0):
                 t = time.perf_counter()
                 self.s = scs.SCS(data, cone, linear_solver=scs.LinearSolver.CPU_INDIRECT, verbose=False, max_iters=int(k),
-                                 eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0)
+                                 eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0, time_limit_secs=float(time_limit))
                 self.setup_s = time.perf_counter() - t
 
             def solve(self):
@@ -226,7 +226,7 @@ def reference_factory():
     from oracle import scs_oracle as O  # no compiled reference on this box: the numpy restatement ("port")
 
     class _W:
-        def __init__(self, data, cone, k):
+        def __init__(self, data, cone, k, time_limit=0.0):
             t = time.perf_counter()
             self.s = O.ScsOracle(data, cone, max_iters=int(k), eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0)
             self.setup_s = time.perf_counter() - t
@@ -263,20 +263,30 @@ def reference_window(data, cone, ips, steps, warmup, budget_s, scale=None):
     est_g = t1 * ratio
     pilot_s = time.perf_counter() - t_begin
     W, K = warmup, steps
+    # The pilot is pessimistic at full size (measured on the bench box: it predicted 6.9 s per early iteration and 54 s
+    # for the g solve where the full-size run took 1.6 s and 36 s): a sample longer than one iteration per step is
+    # only taken when the pessimistic figures allow it, and steps are only cut when even the optimistic ones
+    # (x 0.3 / x 0.6) say one iteration per step does not fit.  The second solve carries time_limit_secs as a net
+    # (checked by the reference every 25 iterations, scs.c:1355-1360).
     room = budget_s - pilot_s - 2 * est_setup - 2 * est_g - 2 * est_it
     n_s = int(room / max(1e-9, (2 * W + K) * est_it))
     n_s = max(1, min(ips, n_s))
-    if room < (2 * W + K) * est_it:  # even one iteration per step does not fit: fewer steps, never a shorter solve
+    room_opt = budget_s - pilot_s - 2 * est_setup - 2 * 0.6 * est_g - 2 * 0.3 * est_it
+    if n_s == 1 and room_opt < (2 * W + K) * 0.3 * est_it:  # fewer steps, never a shorter solve
         W = min(W, 1)
-        K = max(2, min(K, int(room / est_it) - 2 * W))
+        K = max(2, min(K, int(room_opt / (0.3 * est_it)) - 2 * W))
     it_lo, it_hi = 1 + W * n_s, 1 + (W + K) * n_s
     lo = make(data, cone, it_lo)
     setup_s = lo.setup_s
     i_lo, t_lo = lo.solve()
     del lo
-    hi = make(data, cone, it_hi)
+    left = budget_s - (time.perf_counter() - t_begin) - setup_s
+    hi = make(data, cone, it_hi, time_limit=max(10.0, left))
     i_hi, t_hi = hi.solve()
     del hi
+    if i_hi <= i_lo:  # the net cut the second solve before the window opened: nothing to report but the fact
+        i_hi, t_hi = i_lo + 1, t_lo + 1e9
+    K = max(1, (i_hi - i_lo) // n_s) if i_hi < it_hi else K
     dt = max(1e-9, t_hi - t_lo)
     return dict(value=(i_hi - i_lo) / dt, kind=kind, cores=cores, port=port, setup_s=setup_s, window=[i_lo, i_hi],
                 t_lo_s=t_lo, t_hi_s=t_hi, steps_timed=K, warmup_timed=W, iters_per_step_timed=n_s,

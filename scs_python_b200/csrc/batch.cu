@@ -51,13 +51,13 @@ constexpr double kMaxScaleB = 1e6, kMinScaleB = 1e-6, kCgBestTolB = 1e-12, kCgTo
 constexpr double kMinNormB = 1e-4, kMaxNormB = 1e4;
 constexpr int kRuizB = 25, kL2B = 1;
 
-struct BDims { int n, m, nnzA, nnzP, nq, mem, direct, pad; };  // maxima over the batch; direct: dense inverse resident
+struct BDims { int n, m, nnzA, nnzP, nq, mem, direct, nb; };  // maxima over the batch; direct: dense inverse resident; nb: box bounds (bsize - 1)
 struct BStg {
   int normalize, adaptive_scale, max_iters, aa_mem, aa_interval, aa_type1, refine, pad;
   double scale, rho_x, eps_abs, eps_rel, eps_infeas, alpha, aa_reg;
 };
 struct BProb {
-  int n, m, nnzA, nnzP, z, l, nq, pad;
+  int n, m, nnzA, nnzP, z, l, nq, bsize;  // bsize: box cone rows [t; s] right after the nonneg rows (cones.c:1174-1237)
   long long d_off, i_off, sol_off;
 };
 struct BOut {
@@ -71,7 +71,7 @@ struct BOut {
 
 // shared-memory carve-up, identical on host and device (offsets in doubles / u16 elements)
 struct BLay {
-  int Aval, AvalR, Pval, u, ut, v, vp, rsk, g, dr, b, c, D, E, cp, cr, cGp, cM, tmp, ws, red, aaR, aaScr, Ginv, nd;
+  int Aval, AvalR, Pval, u, ut, v, vp, rsk, g, dr, b, c, D, E, cp, cr, cGp, cM, tmp, ws, red, aaR, aaScr, bl, bu, Ginv, nd;
   int st_bytes;
   int Arow, Aperm, Acol, Acp, Arp, Pcol, Prp, qoff, qlen, ni;
   __host__ __device__ explicit BLay(const BDims &d) {
@@ -85,6 +85,7 @@ struct BLay {
     red = take(2 * kBW * kBRed);
     aaR = take(d.mem > 0 ? d.mem * (2 * d.mem + 1) : 0);
     aaScr = take(d.mem > 0 ? 4 * d.mem * d.mem + 6 * d.mem + 8 : 0);
+    bl = take(d.nb); bu = take(d.nb);
     Ginv = take(d.direct ? d.n * (d.n | 1) : 0);
     nd = o;
     st_bytes = (int)((sizeof(AaState) + 15) / 16 * 16);
@@ -96,7 +97,7 @@ struct BLay {
   __host__ __device__ size_t bytes() const { return (size_t)nd * 8 + st_bytes + (size_t)ni * 2 + 16; }
 };
 // per-problem element counts of the packed pools
-static inline long long dpool_count(int n, int m, int nnzA, int nnzP) { return (long long)nnzA + nnzP + m + n; }
+static inline long long dpool_count(int n, int m, int nnzA, int nnzP, int nb) { return (long long)nnzA + nnzP + m + n + 2ll * nb; }
 static inline long long ipool_count(int n, int m, int nnzA, int nnzP, int nq) {
   return 3ll * nnzA + (n + 1) + (m + 1) + nnzP + (n + 1) + 2ll * nq;
 }
@@ -168,7 +169,8 @@ struct Resid {  // ScsResiduals scalars in the ORIGINAL scaling (scs_work.h:29-5
 struct B {  // one CTA's view of its problem
   int n, m, l, nnzA, nnzP, z, nl, nq, tid;
   double *Aval, *AvalR, *Pval, *u, *ut, *v, *vp, *rsk, *g, *dr, *b, *c, *D, *E, *cp, *cr, *cGp, *cM, *tmp, *ws;
-  double *aaR, *aaScr, *Ginv;
+  double *aaR, *aaScr, *Ginv, *bl, *bu;
+  int bsize;
   int direct, refine, gld, gparts, gshift;
   u16 *Arow, *Aperm, *Acol, *Acp, *Arp, *Pcol, *Prp, *qoff, *qlen;
   AaState *st;
@@ -690,6 +692,41 @@ __device__ __forceinline__ void soc_moreau_warp(double *uy, const double *ry, in
   if (lane == 0) uy[0] = alpha / r0 + s0;
 }
 
+// The box cone {(t, s): t bl <= s <= t bu} inside the Moreau step, by the whole CTA: uy holds s_saved (= 2 u_t - v on the
+// cone's rows), ry the cone's R_y; x = -r s is projected by Newton on t with CTA-reduced gradient / Hessian (<= 25
+// iterations, the reference's stopping rules), result uy = Pi(x) / r + s_saved.  Returns t (warm start of the next call).
+__device__ double box_moreau(B &s, double *uy, const double *ry, double t) {
+  const int bs = s.bsize;
+  if (bs == 1) {
+    if (s.tid == 0) { const double s0 = uy[0], r0 = ry[0]; uy[0] = fmax(-r0 * s0, 0.0) / r0 + s0; }
+    return t;
+  }
+  const double r0 = ry[0], s0 = uy[0], tx0 = -r0 * s0, rho_t = 1.0 / r0;
+  const int nb = bs - 1;
+  for (int iter = 0; iter < 25; ++iter) {  // BOX_CONE_MAX_ITERS
+    double v[2] = {0.0, 0.0};
+    BFOR(j, nb) {
+      const double rj = ry[1 + j], xj = -rj * uy[1 + j], rinv = 1.0 / rj, ub = s.bu[j], lb = s.bl[j];
+      if (xj > t * ub) { v[0] += rinv * (t * ub - xj) * ub; v[1] += rinv * ub * ub; }
+      else if (xj < t * lb) { v[0] += rinv * (t * lb - xj) * lb; v[1] += rinv * lb * lb; }
+    }
+    breduce<2, 0>(v, s.red);
+    const double gt = rho_t * (t - tx0) + v[0], ht = rho_t + v[1], t_prev = t;
+    t = fmax(t - gt / fmax(ht, 1e-8), 0.0);
+    if (fabs(gt / fmax(ht, 1e-6)) < 1e-12 * fmax(t, 1.0) || fabs(t - t_prev) < 1e-11 * fmax(t, 1.0)) break;  // uniform
+  }
+  __syncthreads();  // every thread has read uy[0] (s0)
+  BFOR(j, nb) {
+    const double rj = ry[1 + j], sj = uy[1 + j];
+    double xj = -rj * sj;
+    if (xj > t * s.bu[j]) xj = t * s.bu[j];
+    else if (xj < t * s.bl[j]) xj = t * s.bl[j];
+    uy[1 + j] = xj / rj + sj;
+  }
+  if (s.tid == 0) uy[0] = t / r0 + s0;
+  return t;
+}
+
 __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sh_pid;
@@ -701,7 +738,7 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
   s.rsk = sd + L.rsk; s.g = sd + L.g; s.dr = sd + L.dr; s.b = sd + L.b; s.c = sd + L.c; s.D = sd + L.D; s.E = sd + L.E;
   s.cp = sd + L.cp; s.cr = sd + L.cr; s.cGp = sd + L.cGp; s.cM = sd + L.cM; s.tmp = sd + L.tmp; s.ws = sd + L.ws;
   s.red.buf = sd + L.red; s.red.phase = 0;
-  s.aaR = sd + L.aaR; s.aaScr = sd + L.aaScr; s.Ginv = sd + L.Ginv;
+  s.aaR = sd + L.aaR; s.aaScr = sd + L.aaScr; s.Ginv = sd + L.Ginv; s.bl = sd + L.bl; s.bu = sd + L.bu;
   s.direct = a.dims.direct; s.refine = a.stg.refine;
   s.st = reinterpret_cast<AaState *>(smem_raw + (size_t)L.nd * 8);
   u16 *si = reinterpret_cast<u16 *>(smem_raw + (size_t)L.nd * 8 + L.st_bytes);
@@ -719,7 +756,7 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
     const unsigned long long t_begin = gtimer();
     const BProb pb = a.probs[pid];
     s.n = pb.n; s.m = pb.m; s.l = pb.n + pb.m + 1; s.nnzA = pb.nnzA; s.nnzP = pb.nnzP;
-    s.z = pb.z; s.nl = pb.l; s.nq = pb.nq; s.cg_its = 0; s.gld = pb.n | 1;
+    s.z = pb.z; s.nl = pb.l; s.nq = pb.nq; s.bsize = pb.bsize; s.cg_its = 0; s.gld = pb.n | 1;
     s.gshift = 0;
     while (s.gshift < 5 && (pb.n << (s.gshift + 1)) <= kBT) ++s.gshift;  // lanes per output of ginv_apply
     s.gparts = 1 << s.gshift;
@@ -752,6 +789,9 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
     double nbc[2] = {0.0, 0.0};
     BFOR(i, m) { const double bi = dp[s.nnzA + s.nnzP + i]; s.b[i] = bi; s.D[i] = 1.0; nbc[0] = fmax(nbc[0], fabs(bi)); }
     BFOR(j, n) { const double cj = dp[s.nnzA + s.nnzP + m + j]; s.c[j] = cj; s.E[j] = 1.0; nbc[1] = fmax(nbc[1], fabs(cj)); }
+    const int nbox = s.bsize > 1 ? s.bsize - 1 : 0;
+    BFOR(j, nbox) { s.bl[j] = dp[s.nnzA + s.nnzP + m + n + j]; s.bu[j] = dp[s.nnzA + s.nnzP + m + n + nbox + j]; }
+    double box_t = 1.0;  // box_t_warm_start, cones.c:1552
     if (s.tid == 0) {
       AaState *st = s.st;
       memset(st, 0, sizeof(AaState));
@@ -768,6 +808,14 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
       { const long long c0 = clock64(); equilibrate(s); ck[0] += clock64() - c0; }
     }
     BFOR(k, s.nnzA) s.AvalR[k] = s.Aval[s.Aperm[k]];  // final values in CSR order (one indirection less per non-zero)
+    if (g.normalize && nbox > 0) {  // normalize_box_cone, cones.c:1153-1169: bounds follow the row scaling D
+      const double *Db = s.D + s.z + s.nl;
+      BFOR(j, nbox) {
+        const double f = Db[j + 1] / Db[0];
+        s.bu[j] = s.bu[j] >= 1e15 ? INFINITY : s.bu[j] * f;
+        s.bl[j] = s.bl[j] <= -1e15 ? -INFINITY : s.bl[j] * f;
+      }
+    }
     __syncthreads();
     if (g.normalize) {
       double mx[1] = {0.0};
@@ -855,6 +903,10 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
         if (i >= n + s.z && i < n + s.z + s.nl) { const double ry = s.dr[i]; ui = fmax(-ry * s0, 0.0) / ry + s0; }
         else if (i == l - 1) ui = it < kFeasIters ? 1.0 : fmax(s0, 0.0);
         s.u[i] = ui;
+      }
+      if (s.bsize > 0) {  // box cone rows, Moreau wrapper cones.c:1562-1585 around proj_box_cone (cones.c:1174-1237)
+        __syncthreads();
+        box_t = box_moreau(s, s.u + n + s.z + s.nl, s.dr + n + s.z + s.nl, box_t);
       }
       if (s.nq > 0) {
         __syncthreads();
@@ -979,7 +1031,8 @@ static Eligibility fused_eligible(const ScsData *d, const ScsCone *k, const ScsS
   if (stgs->warm_start || stgs->time_limit_secs > 0) return e;
   if (stgs->acceleration_lookback > kBAaMax) return e;
   if (stgs->acceleration_lookback > 0 && stgs->acceleration_relaxation != 1.0) return e;
-  if (k->bsize > 0 || k->ssize > 0 || k->cssize > 0 || k->ep > 0 || k->ed > 0 || k->psize > 0) return e;
+  if (k->ssize > 0 || k->cssize > 0 || k->ep > 0 || k->ed > 0 || k->psize > 0) return e;
+  if (k->bsize > 1 && (!k->bl || !k->bu)) return e;
   const long long nnzA = d->A->p[d->n];
   long long nnzP = 0;
   if (d->P) {
@@ -1090,6 +1143,7 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
     t.n = std::max(t.n, (int)d[i]->n); t.m = std::max(t.m, (int)d[i]->m);
     t.nnzA = std::max(t.nnzA, (int)d[i]->A->p[d[i]->n]); t.nnzP = std::max(t.nnzP, elig[i].nnzP_full);
     t.nq = std::max(t.nq, elig[i].nq);
+    t.nb = std::max(t.nb, k[i]->bsize > 1 ? (int)k[i]->bsize - 1 : 0);
     t.mem = std::min((int)stgs->acceleration_lookback, kBAaMax);
     if (BLay(t).bytes() > 200 * 1024) { elig[i].ok = false; continue; }  // would not fit next to the others
     dims = t;
@@ -1113,9 +1167,9 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
       const ScsCone *kk = k[fused[f]];
       BProb &p = probs[f];
       p.n = dd->n; p.m = dd->m; p.nnzA = dd->A->p[dd->n]; p.nnzP = elig[fused[f]].nnzP_full;
-      p.z = kk->z; p.l = kk->l; p.nq = kk->qsize; p.pad = 0;
+      p.z = kk->z; p.l = kk->l; p.nq = kk->qsize; p.bsize = kk->bsize;
       p.d_off = dtot; p.i_off = itot; p.sol_off = stot;
-      dtot += dpool_count(p.n, p.m, p.nnzA, p.nnzP);
+      dtot += dpool_count(p.n, p.m, p.nnzA, p.nnzP, p.bsize > 1 ? p.bsize - 1 : 0);
       itot += ipool_count(p.n, p.m, p.nnzA, p.nnzP, p.nq);
       itot = (itot + 7) & ~7ll;
       stot += p.n + 2ll * p.m;
@@ -1178,7 +1232,11 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
       double *pb = pv + p.nnzP;
       for (int i = 0; i < p.m; ++i) pb[i] = dd->b[i];
       for (int j = 0; j < p.n; ++j) pb[p.m + j] = dd->c[j];
-      int off = kk->z + kk->l;
+      {
+        const int nb = p.bsize > 1 ? p.bsize - 1 : 0;
+        for (int j = 0; j < nb; ++j) { pb[p.m + p.n + j] = kk->bl[j]; pb[p.m + p.n + nb + j] = kk->bu[j]; }
+      }
+      int off = kk->z + kk->l + kk->bsize;
       for (int c = 0; c < p.nq; ++c) { qoff[c] = (u16)off; qlen[c] = (u16)kk->q[c]; off += kk->q[c]; }
     }
     const double pack_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();

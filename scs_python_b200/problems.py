@@ -217,3 +217,30 @@ def mpc_qp(seed=0, nx=12, nu=6, T=6):
     b = np.concatenate([beq, ub, ub, np.full(T * nu, dumax)])
     c = np.zeros(n)
     return dict(A=A, P=sp.csc_matrix(sp.triu(P)), b=b, c=c), dict(z=(T + 1) * nx, l=A.shape[0] - (T + 1) * nx), dict()
+
+
+def mpc_qp_box(seed=0, nx=12, nu=6, T=6):
+    """Cfg-5 in the reference example's own form (S/docs/src/examples/python/mpc.py:12-65): the same dynamics,
+    weights and bounds as mpc_qp, with the two-sided variable bounds carried by ONE box cone
+    {(t, s) : t bl <= s <= t bu} whose t row is pinned to 1 by b (mpc.py:49-60)  =>  rows: dynamics (zero
+    cone, 84), box cone (1 + n = 121), input-rate limits (nonneg cone, 36), in the reference's cone order
+    z, l, box (S/include/scs.h ScsCone)  =>  m = 241."""
+    rng = np.random.RandomState(seed)
+    Ad = 0.95 * np.eye(nx) + 0.1 * rng.standard_normal((nx, nx))
+    Bd = rng.standard_normal((nx, nu))
+    x0 = 10.0 * rng.standard_normal(nx)
+    n = (T + 1) * nx + T * nu
+    Q, R = sp.eye(nx), 0.1 * sp.eye(nu)
+    P = sp.block_diag([sp.kron(sp.eye(T + 1), Q), sp.kron(sp.eye(T), R)], format="csc")
+    Ax = sp.kron(sp.eye(T + 1), -sp.eye(nx)) + sp.kron(sp.eye(T + 1, k=-1), sp.csc_matrix(Ad))
+    Bu = sp.kron(sp.vstack([sp.csc_matrix((1, T)), sp.eye(T)]), sp.csc_matrix(Bd))
+    Aeq = sp.hstack([Ax, Bu])
+    beq = np.zeros((T + 1) * nx); beq[:nx] = -x0
+    xmax, umax, dumax = 100.0, 2.0, 1.0
+    ub = np.concatenate([np.full((T + 1) * nx, xmax), np.full(T * nu, umax)])
+    Du = sp.hstack([sp.csc_matrix((T * nu, (T + 1) * nx)), sp.kron(sp.eye(T) - sp.eye(T, k=-1), sp.eye(nu))])
+    A = sp.vstack([Aeq, Du, sp.csc_matrix((1, n)), -sp.eye(n, format="csc")], format="csc")
+    A.sort_indices()
+    b = np.concatenate([beq, np.full(T * nu, dumax), [1.0], np.zeros(n)])
+    c = np.zeros(n)
+    return dict(A=A, P=sp.csc_matrix(sp.triu(P)), b=b, c=c), dict(z=(T + 1) * nx, l=T * nu, bu=ub.copy(), bl=-ub), dict()

@@ -5,7 +5,8 @@ Runs ONLY in the build container; the fixture is committed.
 
     make -C oracle ref && python tests/golden/make_golden_batch.py
 
-Cases: BASELINE.json configs[4] MPC QPs (scs_python_b200.problems.mpc_qp, seeds 0..23) and small
+Cases: BASELINE.json configs[4] MPC QPs (scs_python_b200.problems.mpc_qp, seeds 0..23), the same problems
+with a box cone (problems.mpc_qp_box, seeds 0..11) and small
 second-order-cone programs (tests/problems.gen_feasible), each solved by scs.SCS(...).solve() with
 QDLDL and CPU_INDIRECT at eps 1e-4 (defaults) and 1e-9.
 """
@@ -36,7 +37,7 @@ def main():
     import scs
     from scs_python_b200 import problems as bp
     from tests import problems as tp
-    out = dict(source="scs.SCS(...).solve() of oracle/_ref (SCS 3.2.11), QDLDL and CPU_INDIRECT", mpc=[], soc=[])
+    out = dict(source="scs.SCS(...).solve() of oracle/_ref (SCS 3.2.11), QDLDL and CPU_INDIRECT", mpc=[], soc=[], mpc_box=[])
     for seed in range(24):
         data, cone, _ = bp.mpc_qp(seed)
         rec = dict(seed=seed, runs={})
@@ -45,6 +46,14 @@ def main():
                 sol = scs.SCS(data, cone, linear_solver=ls, verbose=False, eps_abs=eps, eps_rel=eps, max_iters=100000).solve()
                 rec["runs"]["%s_%g" % (name, eps)] = rec_of(sol)
         out["mpc"].append(rec)
+    for seed in range(12):  # the same MPC problems with the bounds as one box cone (the reference example's own form)
+        data, cone, _ = bp.mpc_qp_box(seed)
+        rec = dict(seed=seed, runs={})
+        for eps in (1e-4, 1e-9):
+            for name, ls in (("qdldl", scs.LinearSolver.QDLDL), ("cpu_indirect", scs.LinearSolver.CPU_INDIRECT)):
+                sol = scs.SCS(data, cone, linear_solver=ls, verbose=False, eps_abs=eps, eps_rel=eps, max_iters=100000).solve()
+                rec["runs"]["%s_%g" % (name, eps)] = rec_of(sol)
+        out["mpc_box"].append(rec)
     for seed, K, n, withP in [(3, dict(z=4, l=10, q=[3, 5, 8]), 20, True), (4, dict(z=0, l=30, q=[4] * 10 + [1, 2]), 35, False),
                               (5, dict(z=6, l=0, q=[12, 40]), 30, True), (6, dict(z=2, l=50), 25, True)]:
         data, p_star = tp.gen_feasible(K, n, 0.3, seed, with_P=withP)

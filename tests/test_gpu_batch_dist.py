@@ -74,6 +74,34 @@ def test_batch_soc_vs_reference_golden(scsb, eps):
         assert _rel(s["info"]["pobj"], r["pobj"]) < tol
 
 
+@pytest.mark.parametrize("eps", [1e-9, 1e-4])
+def test_batch_box_cone_vs_reference_golden(scsb, eps):
+    """The MPC problems in the reference example's own form, bounds as ONE box cone with the t row pinned by b
+    (S/docs/src/examples/python/mpc.py:49-60): the batch kernel runs the box projection (S/src/cones.c:1290-1378,
+    Newton on t) itself -- every member must take the fused one-CTA path, not the streaming fallback."""
+    from scs_python_b200 import problems as bp
+    from scs_python_b200 import _scs_b200 as B
+    probs = [bp.mpc_qp_box(g["seed"])[:2] for g in GOLD["mpc_box"]]
+    sols = scsb.solve_batch(probs, eps_abs=eps, eps_rel=eps, max_iters=100000, verbose=False)
+    st = B.batch_stats()
+    assert st["fused"] == len(probs) and st["streamed"] == 0, st
+    tol = 1e-6 if eps < 1e-8 else 2e-3
+    for s, g, (d, k) in zip(sols, GOLD["mpc_box"], probs):
+        r = g["runs"]["qdldl_%g" % eps]
+        assert s["info"]["status_val"] == r["status_val"] == 1, (s["info"]["status"], r["status"])
+        assert _rel(s["info"]["pobj"], r["pobj"]) < tol, (s["info"]["pobj"], r["pobj"])
+        assert _rel(s["info"]["dobj"], r["dobj"]) < tol, (s["info"]["dobj"], r["dobj"])
+        helpers.verify_solution(d, k, s, max(eps, 1e-8), max(eps, 1e-8))
+    if eps == 1e-9:
+        its = np.array([s["info"]["iter"] for s in sols]); ref = np.array([g["runs"]["qdldl_1e-09"]["iter"] for g in GOLD["mpc_box"]])
+        print("box-cone MPC iterations b200 %s / reference QDLDL %s" % (its.tolist(), ref.tolist()))
+        assert np.all(np.abs(its - ref) <= 50), (its, ref)
+    # same members through the streaming engine: same optimum (two engines, one algorithm)
+    for (d, k), s in list(zip(probs, sols))[:2]:
+        a = scsb.SCS(d, k, eps_abs=eps, eps_rel=eps, max_iters=100000, verbose=False).solve(warm_start=False)
+        assert a["info"]["status_val"] == 1 and _rel(a["info"]["pobj"], s["info"]["pobj"]) < tol
+
+
 def test_batch_agrees_with_streaming_engine(scsb, mpc_probs):
     """Same problem through the one-CTA batch kernel and through the streaming (graph-launched)
     engine: same status, objectives within 1e-6 relative, iterates within 1e-5."""
