@@ -6,11 +6,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import scs_python_b200 as scsb
 from scs_python_b200 import problems as P
 
-ap = argparse.ArgumentParser(); ap.add_argument("--scale", type=float, default=1.0); a = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--scale", type=float, default=1.0); ap.add_argument("--reps", type=int, default=10); a = ap.parse_args()
 data, cone, _ = P.lasso(int(1_000_000 * a.scale), int(2_000_000 * a.scale), 100, seed=0)
 s = scsb.SCS(data, cone, verbose=False, eps_infeas=1e-12)
 for which in (0, 1):
-    ms, ab = s._solver.bench_spmv(which, 10)
+    ms, ab = s._solver.bench_spmv(which, a.reps)
     pr = s._solver.tiled_profile(which)
     print("op %d: %.3f ms/launch, %.0f GB/s; CTAs %d" % (which, ms, ab / ms / 1e6, len(pr)))
     if len(pr):
