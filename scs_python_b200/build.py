@@ -102,6 +102,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
 if __name__ == "__main__":
     if "--alt" in sys.argv:
-        print(build_alt(0))
+        i = sys.argv.index("--alt")
+        print(build_alt(int(sys.argv[i + 1]) if i + 1 < len(sys.argv) and sys.argv[i + 1].isdigit() else 0))
     else:
         build(force="--force" in sys.argv)

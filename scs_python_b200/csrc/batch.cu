@@ -10,7 +10,8 @@
 //   linear system        warm-started diagonal-PCG on R_x + P + A' R_y^-1 A
 //                        (linsys/cpu/indirect/private.c:50-316), CG tolerance rule scs.c:703-720
 //   tau root             root_plus (scs.c:667-688)
-//   cones                zero / nonneg inline, one warp per second-order cone (cones.c:1242-1271),
+//   cones                zero / nonneg inline, box cone by the CTA (Newton on t, cones.c:1174-1237), one warp per
+//                        second-order cone (cones.c:1242-1271), one thread per exponential / power cone (cone3.cuh),
 //                        Moreau wrapper cones.c:1544-1588
 //   ADMM vector updates  scs.c:739-779
 //   residuals / stop     populate_residual_struct, has_converged, update_scale (scs.c:441-627, 1112-1189)
@@ -22,7 +23,7 @@
 // The grid is persistent: min(count, SMs x resident CTAs) CTAs pull problem indices from an atomic
 // counter, so uneven iteration counts do not leave SMs idle.  No host synchronisation happens
 // between the upload of the packed batch and the download of the solutions.
-// Problems the CTA cannot hold (shared-memory footprint, PSD / exp / power / box cones, warm
+// Problems the CTA cannot hold (shared-memory footprint, PSD cones, warm
 // start, time limit, AA relaxation != 1, lookback > 10) are solved by the streaming engine, one
 // after another -- still on the GPU, never on the host.
 #include <algorithm>
@@ -30,6 +31,7 @@
 #include <numeric>
 
 #include "aa_small.cuh"
+#include "cone3.cuh"
 #include "solver_internal.cuh"
 
 namespace b200 {
@@ -51,13 +53,16 @@ constexpr double kMaxScaleB = 1e6, kMinScaleB = 1e-6, kCgBestTolB = 1e-12, kCgTo
 constexpr double kMinNormB = 1e-4, kMaxNormB = 1e4;
 constexpr int kRuizB = 25, kL2B = 1;
 
-struct BDims { int n, m, nnzA, nnzP, nq, mem, direct, nb; };  // maxima over the batch; direct: dense inverse resident; nb: box bounds (bsize - 1)
+struct BDims { int n, m, nnzA, nnzP, nq, mem, direct, nb, np, tri; };  // maxima over the batch; direct: dense inverse resident; nb: box bounds
+                                                                    // (bsize - 1); nq: cones with a boundary (SOC + exp + power); np: power cones;
+                                                                    // tri: some member has exp / power cones
 struct BStg {
   int normalize, adaptive_scale, max_iters, aa_mem, aa_interval, aa_type1, refine, pad;
   double scale, rho_x, eps_abs, eps_rel, eps_infeas, alpha, aa_reg;
 };
 struct BProb {
   int n, m, nnzA, nnzP, z, l, nq, bsize;  // bsize: box cone rows [t; s] right after the nonneg rows (cones.c:1174-1237)
+  int nsoc, ep, ed, np;                   // nq = nsoc second-order cones followed by ep + ed exponential and np power cones (3 rows each)
   long long d_off, i_off, sol_off;
 };
 struct BOut {
@@ -71,7 +76,7 @@ struct BOut {
 
 // shared-memory carve-up, identical on host and device (offsets in doubles / u16 elements)
 struct BLay {
-  int Aval, AvalR, Pval, u, ut, v, vp, rsk, g, dr, b, c, D, E, cp, cr, cGp, cM, tmp, ws, red, aaR, aaScr, bl, bu, Ginv, nd;
+  int Aval, AvalR, Pval, u, ut, v, vp, rsk, g, dr, b, c, D, E, cp, cr, cGp, cM, tmp, ws, red, aaR, aaScr, bl, bu, pw, Ginv, nd;
   int st_bytes;
   int Arow, Aperm, Acol, Acp, Arp, Pcol, Prp, qoff, qlen, ni;
   __host__ __device__ explicit BLay(const BDims &d) {
@@ -85,7 +90,7 @@ struct BLay {
     red = take(2 * kBW * kBRed);
     aaR = take(d.mem > 0 ? d.mem * (2 * d.mem + 1) : 0);
     aaScr = take(d.mem > 0 ? 4 * d.mem * d.mem + 6 * d.mem + 8 : 0);
-    bl = take(d.nb); bu = take(d.nb);
+    bl = take(d.nb); bu = take(d.nb); pw = take(d.np);
     Ginv = take(d.direct ? d.n * (d.n | 1) : 0);
     nd = o;
     st_bytes = (int)((sizeof(AaState) + 15) / 16 * 16);
@@ -97,7 +102,7 @@ struct BLay {
   __host__ __device__ size_t bytes() const { return (size_t)nd * 8 + st_bytes + (size_t)ni * 2 + 16; }
 };
 // per-problem element counts of the packed pools
-static inline long long dpool_count(int n, int m, int nnzA, int nnzP, int nb) { return (long long)nnzA + nnzP + m + n + 2ll * nb; }
+static inline long long dpool_count(int n, int m, int nnzA, int nnzP, int nb, int np) { return (long long)nnzA + nnzP + m + n + 2ll * nb + np; }
 static inline long long ipool_count(int n, int m, int nnzA, int nnzP, int nq) {
   return 3ll * nnzA + (n + 1) + (m + 1) + nnzP + (n + 1) + 2ll * nq;
 }
@@ -169,8 +174,8 @@ struct Resid {  // ScsResiduals scalars in the ORIGINAL scaling (scs_work.h:29-5
 struct B {  // one CTA's view of its problem
   int n, m, l, nnzA, nnzP, z, nl, nq, tid;
   double *Aval, *AvalR, *Pval, *u, *ut, *v, *vp, *rsk, *g, *dr, *b, *c, *D, *E, *cp, *cr, *cGp, *cM, *tmp, *ws;
-  double *aaR, *aaScr, *Ginv, *bl, *bu;
-  int bsize;
+  double *aaR, *aaScr, *Ginv, *bl, *bu, *pw;
+  int bsize, nsoc, ep, ed, np;
   int direct, refine, gld, gparts, gshift;
   u16 *Arow, *Aperm, *Acol, *Acp, *Arp, *Pcol, *Prp, *qoff, *qlen;
   AaState *st;
@@ -398,7 +403,7 @@ __device__ void update_work_cache(B &s) {
   lin_solve(s, s.g, nullptr, kCgBestTolB);
 }
 
-// enforce_cone_boundaries (cones.c:366-379) on a length-m vector: only second-order cones have size > 1 here
+// enforce_cone_boundaries (cones.c:366-379) on a length-m vector: second-order, exponential and power cones have size > 1 here
 template <bool MEAN>
 __device__ void enforce_soc(B &s, double *vec) {
   const int lane = s.tid & 31, w = s.tid >> 5;
@@ -727,6 +732,8 @@ __device__ double box_moreau(B &s, double *uy, const double *ry, double t) {
   return t;
 }
 
+// kTri: the batch holds exponential / power cones (their root finders are kept out of the plain instantiation)
+template <bool kTri>
 __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sh_pid;
@@ -738,7 +745,7 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
   s.rsk = sd + L.rsk; s.g = sd + L.g; s.dr = sd + L.dr; s.b = sd + L.b; s.c = sd + L.c; s.D = sd + L.D; s.E = sd + L.E;
   s.cp = sd + L.cp; s.cr = sd + L.cr; s.cGp = sd + L.cGp; s.cM = sd + L.cM; s.tmp = sd + L.tmp; s.ws = sd + L.ws;
   s.red.buf = sd + L.red; s.red.phase = 0;
-  s.aaR = sd + L.aaR; s.aaScr = sd + L.aaScr; s.Ginv = sd + L.Ginv; s.bl = sd + L.bl; s.bu = sd + L.bu;
+  s.aaR = sd + L.aaR; s.aaScr = sd + L.aaScr; s.Ginv = sd + L.Ginv; s.bl = sd + L.bl; s.bu = sd + L.bu; s.pw = sd + L.pw;
   s.direct = a.dims.direct; s.refine = a.stg.refine;
   s.st = reinterpret_cast<AaState *>(smem_raw + (size_t)L.nd * 8);
   u16 *si = reinterpret_cast<u16 *>(smem_raw + (size_t)L.nd * 8 + L.st_bytes);
@@ -756,7 +763,7 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
     const unsigned long long t_begin = gtimer();
     const BProb pb = a.probs[pid];
     s.n = pb.n; s.m = pb.m; s.l = pb.n + pb.m + 1; s.nnzA = pb.nnzA; s.nnzP = pb.nnzP;
-    s.z = pb.z; s.nl = pb.l; s.nq = pb.nq; s.bsize = pb.bsize; s.cg_its = 0; s.gld = pb.n | 1;
+    s.z = pb.z; s.nl = pb.l; s.nq = pb.nq; s.bsize = pb.bsize; s.nsoc = pb.nsoc; s.ep = pb.ep; s.ed = pb.ed; s.np = pb.np; s.cg_its = 0; s.gld = pb.n | 1;
     s.gshift = 0;
     while (s.gshift < 5 && (pb.n << (s.gshift + 1)) <= kBT) ++s.gshift;  // lanes per output of ginv_apply
     s.gparts = 1 << s.gshift;
@@ -791,6 +798,7 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
     BFOR(j, n) { const double cj = dp[s.nnzA + s.nnzP + m + j]; s.c[j] = cj; s.E[j] = 1.0; nbc[1] = fmax(nbc[1], fabs(cj)); }
     const int nbox = s.bsize > 1 ? s.bsize - 1 : 0;
     BFOR(j, nbox) { s.bl[j] = dp[s.nnzA + s.nnzP + m + n + j]; s.bu[j] = dp[s.nnzA + s.nnzP + m + n + nbox + j]; }
+    BFOR(j, s.np) s.pw[j] = dp[s.nnzA + s.nnzP + m + n + 2 * nbox + j];
     double box_t = 1.0;  // box_t_warm_start, cones.c:1552
     if (s.tid == 0) {
       AaState *st = s.st;
@@ -910,8 +918,20 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
       }
       if (s.nq > 0) {
         __syncthreads();
-        for (int cidx = warp; cidx < s.nq; cidx += kBW)
+        for (int cidx = warp; cidx < s.nsoc; cidx += kBW)
           soc_moreau_warp(s.u + n + s.qoff[cidx], s.dr + n + s.qoff[cidx], s.qlen[cidx], lane);
+        if (kTri) {  // exponential / power cones, one thread per cone: x = -R s, project, x / r + s (cones.c:1562-1585)
+          for (int cidx = s.nsoc + s.tid; cidx < s.nq; cidx += kBT) {
+            const int t3 = cidx - s.nsoc;
+            double *uy = s.u + n + s.qoff[cidx];
+            const double *ry = s.dr + n + s.qoff[cidx];
+            const double s0 = uy[0], s1 = uy[1], s2 = uy[2];
+            double v3[3] = {-ry[0] * s0, -ry[1] * s1, -ry[2] * s2};
+            const int kind = t3 < s.ep ? 1 : (t3 < s.ep + s.ed ? 0 : -1);
+            proj_cone3(v3, kind, kind < 0 ? s.pw[t3 - s.ep - s.ed] : 0.0);
+            uy[0] = v3[0] / ry[0] + s0; uy[1] = v3[1] / ry[1] + s1; uy[2] = v3[2] / ry[2] + s2;
+          }
+        }
       }
       __syncthreads();
       BFOR(i, l) s.rsk[i] = (s.v[i] + s.u[i] - 2.0 * s.ut[i]) * s.dr[i];  // compute_rsk, scs.c:739-744
@@ -1024,14 +1044,15 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
 }
 
 // ------------------------------------------------------------------------------- host ----
-struct Eligibility { bool ok; int nnzP_full, nq; };
+struct Eligibility { bool ok; int nnzP_full, nq, n3; };
 
 static Eligibility fused_eligible(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
-  Eligibility e{false, 0, 0};
+  Eligibility e{false, 0, 0, 0};
   if (stgs->warm_start || stgs->time_limit_secs > 0) return e;
   if (stgs->acceleration_lookback > kBAaMax) return e;
   if (stgs->acceleration_lookback > 0 && stgs->acceleration_relaxation != 1.0) return e;
-  if (k->ssize > 0 || k->cssize > 0 || k->ep > 0 || k->ed > 0 || k->psize > 0) return e;
+  if (k->ssize > 0 || k->cssize > 0) return e;
+  if (k->psize > 0 && !k->p) return e;
   if (k->bsize > 1 && (!k->bl || !k->bu)) return e;
   const long long nnzA = d->A->p[d->n];
   long long nnzP = 0;
@@ -1041,7 +1062,8 @@ static Eligibility fused_eligible(const ScsData *d, const ScsCone *k, const ScsS
   }
   if (d->n >= 65535 || d->m >= 65535 || nnzA >= 65535 || nnzP >= 65535) return e;
   e.nnzP_full = (int)nnzP;
-  e.nq = k->qsize;
+  e.n3 = (int)(k->ep + k->ed + k->psize);
+  e.nq = (int)k->qsize + e.n3;
   e.ok = true;
   return e;
 }
@@ -1128,7 +1150,7 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
   // ---- classify
   std::vector<int> fused;
   std::vector<Eligibility> elig((size_t)count);
-  BDims dims{0, 0, 0, 0, 0, 0, 0, 0};
+  BDims dims{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < count; ++i) {
     if (!d[i] || !k[i] || !sol[i] || validate_problem(d[i], k[i], stgs) < 0) {
       populate_on_failure(d[i] ? d[i]->m : -1, d[i] ? d[i]->n : -1, sol[i], &info[i], SCS_FAILED, "failure");
@@ -1144,6 +1166,8 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
     t.nnzA = std::max(t.nnzA, (int)d[i]->A->p[d[i]->n]); t.nnzP = std::max(t.nnzP, elig[i].nnzP_full);
     t.nq = std::max(t.nq, elig[i].nq);
     t.nb = std::max(t.nb, k[i]->bsize > 1 ? (int)k[i]->bsize - 1 : 0);
+    t.np = std::max(t.np, (int)k[i]->psize);
+    t.tri = t.tri || elig[i].n3 > 0;
     t.mem = std::min((int)stgs->acceleration_lookback, kBAaMax);
     if (BLay(t).bytes() > 200 * 1024) { elig[i].ok = false; continue; }  // would not fit next to the others
     dims = t;
@@ -1167,9 +1191,11 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
       const ScsCone *kk = k[fused[f]];
       BProb &p = probs[f];
       p.n = dd->n; p.m = dd->m; p.nnzA = dd->A->p[dd->n]; p.nnzP = elig[fused[f]].nnzP_full;
-      p.z = kk->z; p.l = kk->l; p.nq = kk->qsize; p.bsize = kk->bsize;
+      p.z = kk->z; p.l = kk->l; p.bsize = kk->bsize;
+      p.nsoc = kk->qsize; p.ep = kk->ep; p.ed = kk->ed; p.np = kk->psize;
+      p.nq = p.nsoc + p.ep + p.ed + p.np;
       p.d_off = dtot; p.i_off = itot; p.sol_off = stot;
-      dtot += dpool_count(p.n, p.m, p.nnzA, p.nnzP, p.bsize > 1 ? p.bsize - 1 : 0);
+      dtot += dpool_count(p.n, p.m, p.nnzA, p.nnzP, p.bsize > 1 ? p.bsize - 1 : 0, p.np);
       itot += ipool_count(p.n, p.m, p.nnzA, p.nnzP, p.nq);
       itot = (itot + 7) & ~7ll;
       stot += p.n + 2ll * p.m;
@@ -1235,9 +1261,11 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
       {
         const int nb = p.bsize > 1 ? p.bsize - 1 : 0;
         for (int j = 0; j < nb; ++j) { pb[p.m + p.n + j] = kk->bl[j]; pb[p.m + p.n + nb + j] = kk->bu[j]; }
+        for (int j = 0; j < p.np; ++j) pb[p.m + p.n + 2 * nb + j] = kk->p[j];
       }
       int off = kk->z + kk->l + kk->bsize;
-      for (int c = 0; c < p.nq; ++c) { qoff[c] = (u16)off; qlen[c] = (u16)kk->q[c]; off += kk->q[c]; }
+      for (int c = 0; c < p.nsoc; ++c) { qoff[c] = (u16)off; qlen[c] = (u16)kk->q[c]; off += kk->q[c]; }
+      for (int c = p.nsoc; c < p.nq; ++c) { qoff[c] = (u16)off; qlen[c] = 3; off += 3; }  // ep, ed, power cones, in the reference's order (no PSD members here)
     }
     const double pack_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
     // ---- device
@@ -1254,9 +1282,10 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
 #define BCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { fprintf(stderr, "libscsb200: batch: %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); rc = -1; } } while (0)
     if (!ar.st) BCK(cudaStreamCreateWithFlags(&ar.st, cudaStreamNonBlocking));
     st = ar.st;
-    BCK(cudaFuncSetAttribute(k_batch_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = dims.tri ? k_batch_solve<true> : k_batch_solve<false>;
+    BCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    if (!rc) BCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_batch_solve, kBT, smem));
+    if (!rc) BCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBT, smem));
     if (!rc && occ < 1) { fprintf(stderr, "libscsb200: batch: kernel does not fit (%zu B shared memory)\n", smem); rc = -1; }
     const int grid = rc ? 0 : std::min(nf, sms * occ);
     const size_t aa_stride = (aaws_count(dims) + 1) & ~(size_t)1;
@@ -1290,7 +1319,7 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
       if (!ar.e0) { BCK(cudaEventCreate(&ar.e0)); BCK(cudaEventCreate(&ar.e1)); }
       e0 = ar.e0; e1 = ar.e1;
       BCK(cudaEventRecord(e0, st));
-      k_batch_solve<<<grid, kBT, smem, st>>>(a);
+      kern<<<grid, kBT, smem, st>>>(a);
       BCK(cudaGetLastError());
       BCK(cudaEventRecord(e1, st));
       BCK(cudaMemcpyAsync(h_sol, d_sol, sizeof(double) * (size_t)stot, cudaMemcpyDeviceToHost, st));

@@ -513,7 +513,12 @@ int TiledOp::build(Ctx &c, const CsrDev &m1, const CsrDev *m2, bool force) {
       const char *e = getenv("SCS_B200_TILED_U");  // groups per register buffer of the streaming kernel: 8 or 6
       variant = (e && atoi(e) == 6) ? 1 : 0;      // (12 was measured 15 % slower: 122 registers, profiles/r2c_*)
       const char *e2 = getenv("SCS_B200_TILED_EB");
-      epi_eb = (e2 && atoi(e2) == 8) ? 8 : 4;
+      // epilogue pass (SCS_B200_TILED_EB): 1 = chunked / entry-parallel short rows, 0 = the same with 8 entries per thread
+      // batched, 4 / 8 = row-parallel with that many rows in flight per thread
+      epi_eb = (e2 && *e2) ? atoi(e2) : -1;
+      // default: two-source operators (Gp) take the chunked kernel, single-source ones (A p) the row-parallel one;
+      // the forms differ by ~1 % of a product (profiles/r2q_spmv_epilogue_forms.txt)
+      if (epi_eb != 0 && epi_eb != 1 && epi_eb != 4 && epi_eb != 8) epi_eb = m2 ? 1 : 4;
     }
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) break;
     lap("plan+upload");

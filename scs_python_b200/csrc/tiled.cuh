@@ -51,9 +51,15 @@ namespace b200 {
 //      warps per scheduler instead of four.
 // Measured on the bench workload (profiles/r2e_spmv_tile*.txt): Gp product 0.437 ms (cfg 0) -> 0.389 ms (cfg 1),
 // A p 0.406 -> 0.366 ms, although cfg 1 stages twice the x-slice bytes (8 kTC per cell): the kernel is bound by
-// latency, not by L2 -> SM bytes.  cfg 1 is the default; -DB200_TILED_CFG=0 rebuilds the round-1 geometry.
+// latency, not by L2 -> SM bytes.
+//   4: cfg 0's tile (16384 x 4096) with cfg 1's 32 warps (512 rows each), 2 stages of 32 KB: half the x-slice bytes per
+//      cell of cfg 1 at the same shared-memory footprint (192 KB).  Gp product 0.390 -> 0.376 ms, A p unchanged
+//      (profiles/r2o_spmv_tile_geometries.txt).  DEFAULT.
+//   2: as 4 with 3 stages (224 KB of shared memory): slower than either (0.418 ms) -- nothing is left of the L1 for
+//      the entry stream.
+// -DB200_TILED_CFG=0 / 1 rebuild the earlier geometries (python -m scs_python_b200.build --alt k).
 #ifndef B200_TILED_CFG
-#define B200_TILED_CFG 1
+#define B200_TILED_CFG 4
 #endif
 #if B200_TILED_CFG == 1
 constexpr int kTR = 8192;              // rows per row bin
@@ -61,6 +67,12 @@ constexpr int kTC = 8192;              // columns per column bin
 constexpr int kTW = 32;                // warps per CTA
 constexpr int kTStages = 2;            // x-slice stages
 constexpr int kTU0 = 4, kTU1 = 3;      // groups per register buffer of the two streaming-kernel variants
+#elif B200_TILED_CFG == 2 || B200_TILED_CFG == 4  // cfg 0's tile with 32 warps (512 rows each): half the x-slice bytes of cfg 1
+constexpr int kTR = 16384;
+constexpr int kTC = 4096;
+constexpr int kTW = 32;
+constexpr int kTStages = B200_TILED_CFG == 2 ? 3 : 2;
+constexpr int kTU0 = 4, kTU1 = 3;
 #else
 constexpr int kTR = 16384;             // rows per row bin
 constexpr int kTC = 4096;              // columns per column bin
@@ -113,7 +125,7 @@ struct TiledOp {
   std::vector<int> cta_items;
   bool has_tiled = false;  // false: every row bin is a short-row bin (the epilogue pass does it all)
   int variant = 0;         // streaming-kernel variant (tiled_kernel<variant>: groups in flight per warp)
-  int epi_eb = 4;          // rows per thread in flight in the epilogue pass (4 or 8)
+  int epi_eb = 1;          // epilogue pass: 1 / 0 = chunked kernel (plain / batched entry loop); 4 / 8 = row-parallel kernel
   CsrDev m1, m2;
   bool has2 = false;
   // Build from CSR(M1) [and CSR(M2) with the same row count, acting on a second vector]:
@@ -348,6 +360,128 @@ tiled_epilogue_kernel(TiledDev T, CsrDev m1, CsrDev m2, int has2, const double *
   epi.finish(st, ws, S);
 }
 
+// Epilogue pass, chunked form (default).  A CTA takes kEpChunk = 4 x 256 consecutive rows at a time; kTR is a
+// multiple of the chunk, so the chunk lies in ONE row bin and the bin's kind is CTA-uniform.  Tiled bins: as
+// above (pieces added in piece order).  Short-row bins: the chunk's CSR entries are one contiguous range of
+// each source matrix, so the products val * x[idx] are formed ENTRY-parallel -- every thread issues independent,
+// coalesced idx / val loads followed by one gather each -- into shared memory, and each row then adds its own
+// products in entry order (deterministic).  The row-parallel form above walks ptr -> idx/val -> x row after
+// row: nine dependent DRAM latencies per batch of four rows (profiles/r2n_tiled_g_ncu_full.txt: 43 % DRAM, 78 %
+// of the cycles no eligible warp); here the chain is ptr -> idx -> x once per chunk.  Measured
+// (profiles/r2q_spmv_epilogue_forms.txt, r2p_epilogue_ncu.txt): 67 -> 63 us for the Gp epilogue (two sources),
+// 45 -> 52 us for the A p one (single source: the two barriers cost more than the chain), so tiled.cu picks the
+// form per operator; batching eight entries per thread ahead of the gathers (kEpUnr = 8) changes nothing -- the
+// pass is no longer bound by its dependent chain but by 12 interleaved DRAM streams at ~3.7 TB/s.
+constexpr int kEpRows = 4;                      // rows per thread
+constexpr int kEpChunk = kThreads * kEpRows;   // rows per CTA step
+constexpr int kEpCap = 4096;                    // staged products per chunk (32 KB); larger chunks: row-parallel path
+static_assert(kTR % kEpChunk == 0, "a chunk must not straddle row bins");
+template <class Epi, int kEpUnr>
+__global__ void __launch_bounds__(kThreads, 4)
+tiled_epilogue_chunk_kernel(TiledDev T, CsrDev m1, CsrDev m2, int has2, const double *__restrict__ x1,
+                            const double *x2, Epi epi, RedWs ws, DevScalars *S, const int *skip) {
+  if (skip != nullptr && *skip != 0) return;
+  __shared__ double prod[kEpCap];
+  typename Epi::State st;
+  epi.init(st);
+  const int nchunks = (T.nrows + kEpChunk - 1) / kEpChunk;
+  for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int r0 = ch * kEpChunk, r1 = min(T.nrows, r0 + kEpChunk);
+    const int2 bi = T.binfo[r0 / kTR];
+    const bool direct = bi.y == 0 && T.ydir == nullptr;  // CTA-uniform, like everything derived from it
+    int a0 = 0, nA = 0, b0 = 0, nB = 0;
+    if (direct) {
+      a0 = m1.ptr[r0]; nA = m1.ptr[r1] - a0;
+      if (has2) { b0 = m2.ptr[r0]; nB = m2.ptr[r1] - b0; }
+    }
+    const int nT = nA + nB;
+    const bool staged = direct && nT <= kEpCap;
+    if (staged) {
+      // both sources as one index space, kEpUnr entries per thread in flight: all idx / val loads of a batch are
+      // issued before the first gather (r2p ncu source page: an un-batched loop serialises idx -> x per entry)
+      for (int j0 = threadIdx.x; j0 < nT; j0 += kEpUnr * kThreads) {
+        int cc[kEpUnr];
+        double vv[kEpUnr];
+#pragma unroll
+        for (int u = 0; u < kEpUnr; ++u) {
+          const int j = j0 + u * kThreads;
+          cc[u] = 0; vv[u] = 0.0;
+          if (j < nA) { cc[u] = __ldcs(m1.idx + a0 + j); vv[u] = __ldcs(m1.val + a0 + j); }
+          else if (j < nT) { cc[u] = __ldcs(m2.idx + b0 + (j - nA)); vv[u] = __ldcs(m2.val + b0 + (j - nA)); }
+        }
+#pragma unroll
+        for (int u = 0; u < kEpUnr; ++u) {
+          const int j = j0 + u * kThreads;
+          if (j < nA) prod[j] = vv[u] * __ldg(x1 + cc[u]);
+          else if (j < nT) prod[j] = vv[u] * __ldg(x2 + cc[u]);
+        }
+      }
+    }
+    typename Epi::Pre pre[kEpRows];
+    double acc[kEpRows];
+#pragma unroll
+    for (int k = 0; k < kEpRows; ++k) {
+      const int row = r0 + threadIdx.x + k * kThreads;
+      acc[k] = 0.0;
+      if (row < r1) pre[k] = epi.load(row);
+    }
+    if (bi.y != 0) {
+#pragma unroll
+      for (int k = 0; k < kEpRows; ++k) {
+        const int row = r0 + threadIdx.x + k * kThreads;
+        if (row < r1) {
+          const double *src = T.partial + (size_t)bi.x * kTR + (row % kTR);
+          double a = 0.0;
+          for (int p = 0; p < bi.y; ++p) a += __ldcs(src + (size_t)p * kTR);
+          acc[k] = a;
+        }
+      }
+    } else if (!direct) {
+#pragma unroll
+      for (int k = 0; k < kEpRows; ++k) {
+        const int row = r0 + threadIdx.x + k * kThreads;
+        if (row < r1) acc[k] = __ldcs(T.ydir + row);
+      }
+    } else {
+      int sA[kEpRows], eA[kEpRows], sB[kEpRows], eB[kEpRows];
+#pragma unroll
+      for (int k = 0; k < kEpRows; ++k) {
+        const int row = r0 + threadIdx.x + k * kThreads;
+        sA[k] = eA[k] = sB[k] = eB[k] = 0;
+        if (row < r1) {
+          sA[k] = m1.ptr[row]; eA[k] = m1.ptr[row + 1];
+          if (has2) { sB[k] = m2.ptr[row]; eB[k] = m2.ptr[row + 1]; }
+        }
+      }
+      if (staged) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kEpRows; ++k) {
+          double a = 0.0;
+          for (int j = sA[k]; j < eA[k]; ++j) a += prod[j - a0];
+          for (int j = sB[k]; j < eB[k]; ++j) a += prod[nA + j - b0];
+          acc[k] = a;
+        }
+        __syncthreads();  // prod is free for the next chunk
+      } else {
+#pragma unroll
+        for (int k = 0; k < kEpRows; ++k) {
+          double a = 0.0;
+          for (int j = sA[k]; j < eA[k]; ++j) a = fma(__ldcs(m1.val + j), __ldg(x1 + __ldcs(m1.idx + j)), a);
+          for (int j = sB[k]; j < eB[k]; ++j) a = fma(__ldcs(m2.val + j), __ldg(x2 + __ldcs(m2.idx + j)), a);
+          acc[k] = a;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kEpRows; ++k) {
+      const int row = r0 + threadIdx.x + k * kThreads;
+      if (row < r1) epi.apply(st, row, acc[k], pre[k]);
+    }
+  }
+  epi.finish(st, ws, S);
+}
+
 // Short-row bins (identity / bound blocks) multiplied out row by row straight from the CSR arrays: raw
 // products into T.ydir.  Launched on the workspace's side stream so that it runs in the shadow of the
 // streaming kernel (which leaves 3/4 of every SM's thread slots idle by construction).
@@ -419,7 +553,17 @@ inline int tiled_launch(const TiledOp &op, const double *x1, const double *x2, E
   }
   const long long blocks = ((long long)op.d.nrows + kThreads - 1) / kThreads;
   const int grid = (int)(blocks < c.grid_ew() ? (blocks > 0 ? blocks : 1) : c.grid_ew());
-  if (op.epi_eb == 8)
+  if (op.epi_eb == 0) {
+    const long long chunks = ((long long)op.d.nrows + kEpChunk - 1) / kEpChunk;
+    const int gridc = (int)(chunks < c.grid_ew() ? (chunks > 0 ? chunks : 1) : c.grid_ew());
+    tiled_epilogue_chunk_kernel<Epi, 8><<<gridc, kThreads, 0, c.stream>>>(T, op.m1, op.m2, op.has2 ? 1 : 0, x1, x2 ? x2 : x1,
+                                                                         epi, c.red, c.S, skip);
+  } else if (op.epi_eb == 1) {
+    const long long chunks = ((long long)op.d.nrows + kEpChunk - 1) / kEpChunk;
+    const int gridc = (int)(chunks < c.grid_ew() ? (chunks > 0 ? chunks : 1) : c.grid_ew());
+    tiled_epilogue_chunk_kernel<Epi, 1><<<gridc, kThreads, 0, c.stream>>>(T, op.m1, op.m2, op.has2 ? 1 : 0, x1, x2 ? x2 : x1,
+                                                                         epi, c.red, c.S, skip);
+  } else if (op.epi_eb == 8)
     tiled_epilogue_kernel<Epi, 8><<<grid, kThreads, 0, c.stream>>>(T, op.m1, op.m2, op.has2 ? 1 : 0, x1, x2 ? x2 : x1, epi,
                                                                    c.red, c.S, skip);
   else

@@ -6,7 +6,7 @@ Runs ONLY in the build container; the fixture is committed.
     make -C oracle ref && python tests/golden/make_golden_batch.py
 
 Cases: BASELINE.json configs[4] MPC QPs (scs_python_b200.problems.mpc_qp, seeds 0..23), the same problems
-with a box cone (problems.mpc_qp_box, seeds 0..11) and small
+with a box cone (problems.mpc_qp_box, seeds 0..11), small programs with exponential / power cones and small
 second-order-cone programs (tests/problems.gen_feasible), each solved by scs.SCS(...).solve() with
 QDLDL and CPU_INDIRECT at eps 1e-4 (defaults) and 1e-9.
 """
@@ -37,7 +37,7 @@ def main():
     import scs
     from scs_python_b200 import problems as bp
     from tests import problems as tp
-    out = dict(source="scs.SCS(...).solve() of oracle/_ref (SCS 3.2.11), QDLDL and CPU_INDIRECT", mpc=[], soc=[], mpc_box=[])
+    out = dict(source="scs.SCS(...).solve() of oracle/_ref (SCS 3.2.11), QDLDL and CPU_INDIRECT", mpc=[], soc=[], mpc_box=[], tri=[])
     for seed in range(24):
         data, cone, _ = bp.mpc_qp(seed)
         rec = dict(seed=seed, runs={})
@@ -63,6 +63,19 @@ def main():
                 sol = scs.SCS(data, K, linear_solver=ls, verbose=False, eps_abs=eps, eps_rel=eps, max_iters=100000).solve()
                 rec["runs"]["%s_%g" % (name, eps)] = rec_of(sol)
         out["soc"].append(rec)
+    # exponential / power cones next to z, l, q (three-row cones, one thread each in the batch kernel)
+    for seed, K, n, withP in [(11, dict(z=3, l=8, q=[4], ep=3, ed=2, p=[0.3, -0.6, 0.5]), 20, True),
+                              (12, dict(z=0, l=10, ep=6), 15, False),
+                              (13, dict(z=2, l=5, q=[3, 6], p=[0.25, -0.75, 0.5, 0.9]), 18, True),
+                              (14, dict(z=2, l=6, ed=5), 14, True),
+                              (15, dict(z=1, l=4, ep=2, ed=2, p=[-0.4, 0.7]), 12, False)]:
+        data, p_star = tp.gen_feasible(K, n, 0.3, seed, with_P=withP)
+        rec = dict(seed=seed, cone=K, n=n, with_P=withP, p_star=p_star, runs={})
+        for eps in (1e-4, 1e-9):
+            for name, ls in (("qdldl", scs.LinearSolver.QDLDL), ("cpu_indirect", scs.LinearSolver.CPU_INDIRECT)):
+                sol = scs.SCS(data, K, linear_solver=ls, verbose=False, eps_abs=eps, eps_rel=eps, max_iters=100000).solve()
+                rec["runs"]["%s_%g" % (name, eps)] = rec_of(sol)
+        out["tri"].append(rec)
     json.dump(out, open(os.path.join(HERE, "batch_ref.json"), "w"), indent=0)
     its = [r["runs"]["cpu_indirect_0.0001"]["iter"] for r in out["mpc"]]
     print("batch_ref.json: %d mpc, %d soc; mpc iters at 1e-4 (indirect): min %d median %d max %d" %

@@ -102,6 +102,42 @@ def test_batch_box_cone_vs_reference_golden(scsb, eps):
         assert a["info"]["status_val"] == 1 and _rel(a["info"]["pobj"], s["info"]["pobj"]) < tol
 
 
+@pytest.mark.parametrize("eps", [1e-9, 1e-4])
+def test_batch_exp_and_power_cones_vs_reference_golden(scsb, eps):
+    """Exponential (primal / dual) and power (primal / dual) cones inside the one-CTA kernel (one thread per cone,
+    the device functions the streaming engine uses: exp_cone.c, cones.c:1276-1324): every member on the fused
+    path; status, objectives and iteration counts against the compiled reference's QDLDL runs, residual /
+    cone-membership criteria recomputed on the host."""
+    from scs_python_b200 import _scs_b200 as B
+    probs = []
+    for g in GOLD["tri"]:
+        d, _ = tp.gen_feasible(g["cone"], g["n"], 0.3, g["seed"], with_P=bool(g["with_P"]))
+        probs.append((d, g["cone"]))
+    sols = scsb.solve_batch(probs, eps_abs=eps, eps_rel=eps, max_iters=100000, verbose=False)
+    st = B.batch_stats()
+    assert st["fused"] == len(probs) and st["streamed"] == 0, st
+    tol = 1e-6 if eps < 1e-8 else 2e-3
+    its, ref = [], []
+    for s, g, (d, k) in zip(sols, GOLD["tri"], probs):
+        r = g["runs"]["qdldl_%g" % eps]
+        assert s["info"]["status_val"] == r["status_val"] == 1, (g["seed"], s["info"]["status"], r["status"])
+        assert _rel(s["info"]["pobj"], r["pobj"]) < tol, (g["seed"], s["info"]["pobj"], r["pobj"])
+        assert _rel(s["info"]["dobj"], r["dobj"]) < tol, (g["seed"], s["info"]["dobj"], r["dobj"])
+        helpers.verify_solution(d, k, s, max(eps, 1e-8), max(eps, 1e-8))
+        its.append(s["info"]["iter"]); ref.append(r["iter"])
+    print("exp / power batch members, eps %g: iterations b200 %s / reference QDLDL %s" % (eps, its, ref))
+    if eps == 1e-9:
+        assert np.all(np.abs(np.array(its) - np.array(ref)) <= 50), (its, ref)
+    # a mixed batch: members with and without three-row cones share one launch
+    from scs_python_b200 import problems as bp
+    mixed = [probs[0], bp.mpc_qp(0)[:2], probs[2], bp.mpc_qp_box(1)[:2]]
+    ms = scsb.solve_batch(mixed, eps_abs=eps, eps_rel=eps, max_iters=100000, verbose=False)
+    assert B.batch_stats()["fused"] == 4
+    assert all(m["info"]["status_val"] == 1 for m in ms)
+    for a, b in ((ms[0], sols[0]), (ms[2], sols[2])):
+        assert _rel(a["info"]["pobj"], b["info"]["pobj"]) < tol
+
+
 def test_batch_agrees_with_streaming_engine(scsb, mpc_probs):
     """Same problem through the one-CTA batch kernel and through the streaming (graph-launched)
     engine: same status, objectives within 1e-6 relative, iterates within 1e-5."""

@@ -79,6 +79,8 @@ def _solve(B, A, Pf, diag_r, b, s, tol):
     dict(seed=4, m=20000, n=5000, dens=0.001, with_P=True, dense_row=True),    # dense row + dense column
     dict(seed=5, m=17000, n=4097, dens=0.003, with_P=True, empty=True),        # odd sizes, empty rows / columns
     dict(seed=6, m=33, n=7, dens=0.5, with_P=False),                           # tiny
+    dict(seed=7, m=40000, n=9000, dens=0.00055, with_P=True),                  # short-row bins of A, ~5 entries per row: chunks above the staging capacity of the epilogue pass
+    dict(seed=8, m=40000, n=9000, dens=0.0003, with_P=True),                   # short-row bins, 2-3 entries per row: staged products, several per row
 ])
 def test_tiled_lin_sys_kkt_residual_and_row_engine_agreement(B, monkeypatch, case):
     A, Pf, diag_r, rng = _kkt_case(**case)

@@ -29,8 +29,12 @@ def main():
     if a.combos:
         combos = [tuple(c.split(",")) for c in a.combos.split(";")]
     ref_obj = None
-    for perm, side, u in combos:
-        os.environ.update(SCS_B200_TILED_DEAL=perm, SCS_B200_TILED_SIDE=side, SCS_B200_TILED_U=u)
+    for combo in combos:
+        perm, side, u = combo[:3]
+        eb = combo[3] if len(combo) > 3 else "-"   # epilogue pass: - = default, 0 / 1 = chunked kernel (batched / not), 4 / 8 = row-parallel
+        os.environ.update(SCS_B200_TILED_DEAL=perm, SCS_B200_TILED_SIDE=side, SCS_B200_TILED_U=u, SCS_B200_TILED_EB=eb)
+        if eb in ("", "-"):   # the library's own per-operator default
+            os.environ.pop("SCS_B200_TILED_EB")
         s = scsb.SCS(data, cone, verbose=False, max_iters=50, eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0)
         inner = s._solver
         a_ms, a_b = inner.bench_spmv(0, a.reps)
@@ -39,7 +43,7 @@ def main():
         obj = r["info"]["pobj"]
         if ref_obj is None:
             ref_obj = obj
-        print(json.dumps(dict(deal=perm, side=side, U=u, a_ms=a_ms, g_ms=g_ms, a_tbs=a_b / a_ms / 1e9, g_tbs=g_b / g_ms / 1e9,
+        print(json.dumps(dict(lib=os.path.basename(os.environ.get('SCS_B200_LIBPATH', 'libscsb200.so')), deal=perm, side=side, U=u, EB=eb, a_ms=a_ms, g_ms=g_ms, a_tbs=a_b / a_ms / 1e9, g_tbs=g_b / g_ms / 1e9,
                               g_frac_of_6553=g_b / g_ms / 1e9 / 6.5536, pobj_50its=obj,
                               pobj_rel_diff=abs(obj - ref_obj) / max(1.0, abs(ref_obj)))), flush=True)
         inner.finish()
