@@ -457,7 +457,7 @@ def run_b200(args):
                    + " (A_g' z_g of this rank's rows; P p + R_x p and p'Gp are a separate pass, the shared block is then "
                      "all-reduced)")
         else:
-            k_g = (("tiled_kernel<0> + tiled_epilogue_kernel<EpiG> (2-D tiled: x-slices by TMA into shared memory, "
+            k_g = (("tiled_kernel<0> + tiled_epilogue_chunk_kernel<EpiG> (2-D tiled: x-slices by TMA into shared memory, "
                     "accumulators in shared memory; the launches are timed as one product)") if tiled
                    else "row_kernel<ElemMul,ElemMul,EpiG,DUAL>") + " (Gp = A' z + P p + R_x p, p'Gp fused)"
         k_a = ("tiled_kernel<0> + tiled_epilogue_kernel<EpiScaleRy>" if eng.get("tiled_a")
