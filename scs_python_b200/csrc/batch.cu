@@ -11,7 +11,7 @@
 //                        (linsys/cpu/indirect/private.c:50-316), CG tolerance rule scs.c:703-720
 //   tau root             root_plus (scs.c:667-688)
 //   cones                zero / nonneg inline, box cone by the CTA (Newton on t, cones.c:1174-1237), one warp per
-//                        second-order cone (cones.c:1242-1271), one thread per exponential / power cone (cone3.cuh),
+//                        second-order cone (cones.c:1242-1271), one thread per exponential / power cone (cone3.cuh), one warp per PSD cone (Jacobi, order <= 32),
 //                        Moreau wrapper cones.c:1544-1588
 //   ADMM vector updates  scs.c:739-779
 //   residuals / stop     populate_residual_struct, has_converged, update_scale (scs.c:441-627, 1112-1189)
@@ -23,7 +23,7 @@
 // The grid is persistent: min(count, SMs x resident CTAs) CTAs pull problem indices from an atomic
 // counter, so uneven iteration counts do not leave SMs idle.  No host synchronisation happens
 // between the upload of the packed batch and the download of the solutions.
-// Problems the CTA cannot hold (shared-memory footprint, PSD cones, warm
+// Problems the CTA cannot hold (shared-memory footprint, PSD cones of order > 32, complex PSD cones, warm
 // start, time limit, AA relaxation != 1, lookback > 10) are solved by the streaming engine, one
 // after another -- still on the GPU, never on the host.
 #include <algorithm>
@@ -53,16 +53,17 @@ constexpr double kMaxScaleB = 1e6, kMinScaleB = 1e-6, kCgBestTolB = 1e-12, kCgTo
 constexpr double kMinNormB = 1e-4, kMaxNormB = 1e4;
 constexpr int kRuizB = 25, kL2B = 1;
 
-struct BDims { int n, m, nnzA, nnzP, nq, mem, direct, nb, np, tri; };  // maxima over the batch; direct: dense inverse resident; nb: box bounds
+struct BDims { int n, m, nnzA, nnzP, nq, mem, direct, nb, np, tri, ds, pad; };  // maxima over the batch; direct: dense inverse resident; nb: box bounds
                                                                     // (bsize - 1); nq: cones with a boundary (SOC + exp + power); np: power cones;
-                                                                    // tri: some member has exp / power cones
+                                                                    // tri: some member has exp / power / PSD cones; ds: largest PSD order
 struct BStg {
   int normalize, adaptive_scale, max_iters, aa_mem, aa_interval, aa_type1, refine, pad;
   double scale, rho_x, eps_abs, eps_rel, eps_infeas, alpha, aa_reg;
 };
 struct BProb {
   int n, m, nnzA, nnzP, z, l, nq, bsize;  // bsize: box cone rows [t; s] right after the nonneg rows (cones.c:1174-1237)
-  int nsoc, ep, ed, np;                   // nq = nsoc second-order cones followed by ep + ed exponential and np power cones (3 rows each)
+  int nsoc, ns, ep, ed, np, pad;          // nq = nsoc second-order cones, ns PSD cones (packed lower triangles), ep + ed exponential and
+                                          // np power cones (3 rows each), in the reference's cone order (S/include/scs.h ScsCone)
   long long d_off, i_off, sol_off;
 };
 struct BOut {
@@ -74,9 +75,12 @@ struct BOut {
   long long clk[6];  // cycles: equilibrate, factor, lin-sys, AA, residual checks, whole problem
 };
 
+// PSD cones: per-warp Jacobi workspace (matrix, eigenvectors, one rotation per pair of a round), order <= kBPsdMax
+constexpr int kBPsdMax = 32;
+__host__ __device__ inline int psd_ws_doubles(int d) { return 2 * d * d + 2 * ((d + 1) / 2) + 2; }
 // shared-memory carve-up, identical on host and device (offsets in doubles / u16 elements)
 struct BLay {
-  int Aval, AvalR, Pval, u, ut, v, vp, rsk, g, dr, b, c, D, E, cp, cr, cGp, cM, tmp, ws, red, aaR, aaScr, bl, bu, pw, Ginv, nd;
+  int Aval, AvalR, Pval, u, ut, v, vp, rsk, g, dr, b, c, D, E, cp, cr, cGp, cM, tmp, ws, red, aaR, aaScr, bl, bu, pw, psdw, Ginv, nd;
   int st_bytes;
   int Arow, Aperm, Acol, Acp, Arp, Pcol, Prp, qoff, qlen, ni;
   __host__ __device__ explicit BLay(const BDims &d) {
@@ -91,6 +95,7 @@ struct BLay {
     aaR = take(d.mem > 0 ? d.mem * (2 * d.mem + 1) : 0);
     aaScr = take(d.mem > 0 ? 4 * d.mem * d.mem + 6 * d.mem + 8 : 0);
     bl = take(d.nb); bu = take(d.nb); pw = take(d.np);
+    psdw = take(d.ds > 0 ? kBW * psd_ws_doubles(d.ds) : 0);
     Ginv = take(d.direct ? d.n * (d.n | 1) : 0);
     nd = o;
     st_bytes = (int)((sizeof(AaState) + 15) / 16 * 16);
@@ -174,8 +179,8 @@ struct Resid {  // ScsResiduals scalars in the ORIGINAL scaling (scs_work.h:29-5
 struct B {  // one CTA's view of its problem
   int n, m, l, nnzA, nnzP, z, nl, nq, tid;
   double *Aval, *AvalR, *Pval, *u, *ut, *v, *vp, *rsk, *g, *dr, *b, *c, *D, *E, *cp, *cr, *cGp, *cM, *tmp, *ws;
-  double *aaR, *aaScr, *Ginv, *bl, *bu, *pw;
-  int bsize, nsoc, ep, ed, np;
+  double *aaR, *aaScr, *Ginv, *bl, *bu, *pw, *psdw;
+  int bsize, nsoc, ns, ep, ed, np, psd_ws;
   int direct, refine, gld, gparts, gshift;
   u16 *Arow, *Aperm, *Acol, *Acp, *Arp, *Pcol, *Prp, *qoff, *qlen;
   AaState *st;
@@ -697,6 +702,97 @@ __device__ __forceinline__ void soc_moreau_warp(double *uy, const double *ry, in
   if (lane == 0) uy[0] = alpha / r0 + s0;
 }
 
+// One positive-semidefinite cone of the Moreau step, by one warp (cones.c:991-1148 inside cones.c:1562-1585; replaces
+// dsyevr + dsyrk for the small orders a batch member has).  x = -r s is unpacked (lower triangle, column-major,
+// off-diagonals scaled by sqrt 2) into a d x d matrix in shared memory; classical two-sided Jacobi with the
+// round-robin ordering -- the d/2 disjoint pairs of a round rotate together: angles from the current matrix, then the
+// column updates of all pairs (matrix and eigenvector matrix), then the row updates -- until a sweep finds no
+// off-diagonal entry above 1e-17 ||X||_F; X+ = sum_{lambda_k > 0} lambda_k v_k v_k' is re-packed and u = X+ / r + s.
+__device__ void psd_moreau_warp(double *uy, const double *ry, int len, double *ws, int lane) {
+  if (len <= 0) return;
+  const int d = (int)((sqrt(8.0 * len + 1.0) - 1.0) * 0.5 + 0.5);
+  if (d == 1) {
+    if (lane == 0) { const double s0 = uy[0], r0 = ry[0]; uy[0] = fmax(-r0 * s0, 0.0) / r0 + s0; }
+    return;
+  }
+  double *A = ws, *V = ws + d * d, *cs = V + d * d;
+  const double isq2 = 0.70710678118654752440, sq2 = 1.41421356237309504880;
+  double fro = 0.0;
+  for (int k = lane; k < len; k += 32) {  // packed index k -> (i, j), i >= j
+    int j = 0, rem = k;
+    while (rem >= d - j) { rem -= d - j; ++j; }
+    const int i = j + rem;
+    const double x = -ry[k] * uy[k];
+    const double a = i == j ? x : x * isq2;
+    A[i * d + j] = a; A[j * d + i] = a;
+    fro = fma(i == j ? 1.0 : 2.0, a * a, fro);
+  }
+  for (int k = lane; k < d * d; k += 32) V[k] = (k / d == k % d) ? 1.0 : 0.0;
+  fro = sqrt(warp_sum(fro));
+  __syncwarp();
+  const int de = d + (d & 1), half = de >> 1;
+  const double small = 1e-17 * fro;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double mx = 0.0;
+    for (int r = 0; r < de - 1; ++r) {
+      for (int k = lane; k < half; k += 32) {  // rotation of pair k (Numerical-Recipes form), identity when negligible
+        const int p = k == 0 ? de - 1 : (r + k) % (de - 1), q = k == 0 ? r : (r - k + de - 1) % (de - 1);
+        double c = 1.0, sn = 0.0;
+        if (p < d && q < d) {
+          const double apq = A[p * d + q];
+          mx = fmax(mx, fabs(apq));
+          if (fabs(apq) > small) {
+            const double th = (A[q * d + q] - A[p * d + p]) / (2.0 * apq);
+            const double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+            c = 1.0 / sqrt(t * t + 1.0);
+            sn = t * c;
+          }
+        }
+        cs[2 * k] = c; cs[2 * k + 1] = sn;
+      }
+      __syncwarp();
+      for (int idx = lane; idx < half * d; idx += 32) {  // columns p, q of the matrix and of V
+        const int k = idx / d, i = idx - k * d;
+        const int p = k == 0 ? de - 1 : (r + k) % (de - 1), q = k == 0 ? r : (r - k + de - 1) % (de - 1);
+        const double c = cs[2 * k], sn = cs[2 * k + 1];
+        if (p < d && q < d && sn != 0.0) {
+          const double ap = A[i * d + p], aq = A[i * d + q];
+          A[i * d + p] = c * ap - sn * aq; A[i * d + q] = sn * ap + c * aq;
+          const double vp = V[i * d + p], vq = V[i * d + q];
+          V[i * d + p] = c * vp - sn * vq; V[i * d + q] = sn * vp + c * vq;
+        }
+      }
+      __syncwarp();
+      for (int idx = lane; idx < half * d; idx += 32) {  // rows p, q of the matrix
+        const int k = idx / d, j = idx - k * d;
+        const int p = k == 0 ? de - 1 : (r + k) % (de - 1), q = k == 0 ? r : (r - k + de - 1) % (de - 1);
+        const double c = cs[2 * k], sn = cs[2 * k + 1];
+        if (p < d && q < d && sn != 0.0) {
+          const double ap = A[p * d + j], aq = A[q * d + j];
+          A[p * d + j] = c * ap - sn * aq; A[q * d + j] = sn * ap + c * aq;
+        }
+      }
+      __syncwarp();
+    }
+    mx = warp_max(mx);
+    if (mx <= small) break;  // warp-uniform
+  }
+  for (int k = lane; k < len; k += 32) {
+    int j = 0, rem = k;
+    while (rem >= d - j) { rem -= d - j; ++j; }
+    const int i = j + rem;
+    double x = 0.0;
+    for (int e = 0; e < d; ++e) {
+      const double lam = A[e * d + e];
+      if (lam > 0.0) x = fma(lam * V[i * d + e], V[j * d + e], x);
+    }
+    if (i != j) x *= sq2;
+    const double sk = uy[k];
+    uy[k] = x / ry[k] + sk;
+  }
+  __syncwarp();  // the workspace is reused by this warp's next cone
+}
+
 // The box cone {(t, s): t bl <= s <= t bu} inside the Moreau step, by the whole CTA: uy holds s_saved (= 2 u_t - v on the
 // cone's rows), ry the cone's R_y; x = -r s is projected by Newton on t with CTA-reduced gradient / Hessian (<= 25
 // iterations, the reference's stopping rules), result uy = Pi(x) / r + s_saved.  Returns t (warm start of the next call).
@@ -745,7 +841,7 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
   s.rsk = sd + L.rsk; s.g = sd + L.g; s.dr = sd + L.dr; s.b = sd + L.b; s.c = sd + L.c; s.D = sd + L.D; s.E = sd + L.E;
   s.cp = sd + L.cp; s.cr = sd + L.cr; s.cGp = sd + L.cGp; s.cM = sd + L.cM; s.tmp = sd + L.tmp; s.ws = sd + L.ws;
   s.red.buf = sd + L.red; s.red.phase = 0;
-  s.aaR = sd + L.aaR; s.aaScr = sd + L.aaScr; s.Ginv = sd + L.Ginv; s.bl = sd + L.bl; s.bu = sd + L.bu; s.pw = sd + L.pw;
+  s.aaR = sd + L.aaR; s.aaScr = sd + L.aaScr; s.Ginv = sd + L.Ginv; s.bl = sd + L.bl; s.bu = sd + L.bu; s.pw = sd + L.pw; s.psdw = sd + L.psdw; s.psd_ws = psd_ws_doubles(a.dims.ds);
   s.direct = a.dims.direct; s.refine = a.stg.refine;
   s.st = reinterpret_cast<AaState *>(smem_raw + (size_t)L.nd * 8);
   u16 *si = reinterpret_cast<u16 *>(smem_raw + (size_t)L.nd * 8 + L.st_bytes);
@@ -763,7 +859,7 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
     const unsigned long long t_begin = gtimer();
     const BProb pb = a.probs[pid];
     s.n = pb.n; s.m = pb.m; s.l = pb.n + pb.m + 1; s.nnzA = pb.nnzA; s.nnzP = pb.nnzP;
-    s.z = pb.z; s.nl = pb.l; s.nq = pb.nq; s.bsize = pb.bsize; s.nsoc = pb.nsoc; s.ep = pb.ep; s.ed = pb.ed; s.np = pb.np; s.cg_its = 0; s.gld = pb.n | 1;
+    s.z = pb.z; s.nl = pb.l; s.nq = pb.nq; s.bsize = pb.bsize; s.nsoc = pb.nsoc; s.ns = pb.ns; s.ep = pb.ep; s.ed = pb.ed; s.np = pb.np; s.cg_its = 0; s.gld = pb.n | 1;
     s.gshift = 0;
     while (s.gshift < 5 && (pb.n << (s.gshift + 1)) <= kBT) ++s.gshift;  // lanes per output of ginv_apply
     s.gparts = 1 << s.gshift;
@@ -920,9 +1016,11 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
         __syncthreads();
         for (int cidx = warp; cidx < s.nsoc; cidx += kBW)
           soc_moreau_warp(s.u + n + s.qoff[cidx], s.dr + n + s.qoff[cidx], s.qlen[cidx], lane);
-        if (kTri) {  // exponential / power cones, one thread per cone: x = -R s, project, x / r + s (cones.c:1562-1585)
-          for (int cidx = s.nsoc + s.tid; cidx < s.nq; cidx += kBT) {
-            const int t3 = cidx - s.nsoc;
+        if (kTri) {  // PSD cones: one warp each; exponential / power cones: one thread each (x = -R s, project, x / r + s)
+          for (int cidx = s.nsoc + warp; cidx < s.nsoc + s.ns; cidx += kBW)
+            psd_moreau_warp(s.u + n + s.qoff[cidx], s.dr + n + s.qoff[cidx], s.qlen[cidx], s.psdw + warp * s.psd_ws, lane);
+          for (int cidx = s.nsoc + s.ns + s.tid; cidx < s.nq; cidx += kBT) {
+            const int t3 = cidx - s.nsoc - s.ns;
             double *uy = s.u + n + s.qoff[cidx];
             const double *ry = s.dr + n + s.qoff[cidx];
             const double s0 = uy[0], s1 = uy[1], s2 = uy[2];
@@ -1044,14 +1142,19 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
 }
 
 // ------------------------------------------------------------------------------- host ----
-struct Eligibility { bool ok; int nnzP_full, nq, n3; };
+struct Eligibility { bool ok; int nnzP_full, nq, n3, ds; };
 
 static Eligibility fused_eligible(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
-  Eligibility e{false, 0, 0, 0};
+  Eligibility e{false, 0, 0, 0, 0};
   if (stgs->warm_start || stgs->time_limit_secs > 0) return e;
   if (stgs->acceleration_lookback > kBAaMax) return e;
   if (stgs->acceleration_lookback > 0 && stgs->acceleration_relaxation != 1.0) return e;
-  if (k->ssize > 0 || k->cssize > 0) return e;
+  if (k->cssize > 0) return e;
+  long long ncones = 0;
+  for (int i = 0; i < k->ssize; ++i) {
+    if (k->s[i] < 1 || k->s[i] > kBPsdMax) return e;
+    e.ds = std::max(e.ds, (int)k->s[i]);
+  }
   if (k->psize > 0 && !k->p) return e;
   if (k->bsize > 1 && (!k->bl || !k->bu)) return e;
   const long long nnzA = d->A->p[d->n];
@@ -1063,7 +1166,9 @@ static Eligibility fused_eligible(const ScsData *d, const ScsCone *k, const ScsS
   if (d->n >= 65535 || d->m >= 65535 || nnzA >= 65535 || nnzP >= 65535) return e;
   e.nnzP_full = (int)nnzP;
   e.n3 = (int)(k->ep + k->ed + k->psize);
-  e.nq = (int)k->qsize + e.n3;
+  ncones = (long long)k->qsize + k->ssize + e.n3;
+  if (ncones >= 65535) return e;
+  e.nq = (int)ncones;
   e.ok = true;
   return e;
 }
@@ -1150,7 +1255,7 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
   // ---- classify
   std::vector<int> fused;
   std::vector<Eligibility> elig((size_t)count);
-  BDims dims{0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  BDims dims{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < count; ++i) {
     if (!d[i] || !k[i] || !sol[i] || validate_problem(d[i], k[i], stgs) < 0) {
       populate_on_failure(d[i] ? d[i]->m : -1, d[i] ? d[i]->n : -1, sol[i], &info[i], SCS_FAILED, "failure");
@@ -1167,7 +1272,8 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
     t.nq = std::max(t.nq, elig[i].nq);
     t.nb = std::max(t.nb, k[i]->bsize > 1 ? (int)k[i]->bsize - 1 : 0);
     t.np = std::max(t.np, (int)k[i]->psize);
-    t.tri = t.tri || elig[i].n3 > 0;
+    t.tri = t.tri || elig[i].n3 > 0 || elig[i].ds > 0;
+    t.ds = std::max(t.ds, elig[i].ds);
     t.mem = std::min((int)stgs->acceleration_lookback, kBAaMax);
     if (BLay(t).bytes() > 200 * 1024) { elig[i].ok = false; continue; }  // would not fit next to the others
     dims = t;
@@ -1192,8 +1298,8 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
       BProb &p = probs[f];
       p.n = dd->n; p.m = dd->m; p.nnzA = dd->A->p[dd->n]; p.nnzP = elig[fused[f]].nnzP_full;
       p.z = kk->z; p.l = kk->l; p.bsize = kk->bsize;
-      p.nsoc = kk->qsize; p.ep = kk->ep; p.ed = kk->ed; p.np = kk->psize;
-      p.nq = p.nsoc + p.ep + p.ed + p.np;
+      p.nsoc = kk->qsize; p.ns = kk->ssize; p.ep = kk->ep; p.ed = kk->ed; p.np = kk->psize; p.pad = 0;
+      p.nq = p.nsoc + p.ns + p.ep + p.ed + p.np;
       p.d_off = dtot; p.i_off = itot; p.sol_off = stot;
       dtot += dpool_count(p.n, p.m, p.nnzA, p.nnzP, p.bsize > 1 ? p.bsize - 1 : 0, p.np);
       itot += ipool_count(p.n, p.m, p.nnzA, p.nnzP, p.nq);
@@ -1265,7 +1371,8 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
       }
       int off = kk->z + kk->l + kk->bsize;
       for (int c = 0; c < p.nsoc; ++c) { qoff[c] = (u16)off; qlen[c] = (u16)kk->q[c]; off += kk->q[c]; }
-      for (int c = p.nsoc; c < p.nq; ++c) { qoff[c] = (u16)off; qlen[c] = 3; off += 3; }  // ep, ed, power cones, in the reference's order (no PSD members here)
+      for (int c = 0; c < p.ns; ++c) { const int len = kk->s[c] * (kk->s[c] + 1) / 2; qoff[p.nsoc + c] = (u16)off; qlen[p.nsoc + c] = (u16)len; off += len; }
+      for (int c = p.nsoc + p.ns; c < p.nq; ++c) { qoff[c] = (u16)off; qlen[c] = 3; off += 3; }  // ep, ed, power cones (reference order; complex PSD members take the streaming engine)
     }
     const double pack_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
     // ---- device

@@ -6,7 +6,7 @@ Runs ONLY in the build container; the fixture is committed.
     make -C oracle ref && python tests/golden/make_golden_batch.py
 
 Cases: BASELINE.json configs[4] MPC QPs (scs_python_b200.problems.mpc_qp, seeds 0..23), the same problems
-with a box cone (problems.mpc_qp_box, seeds 0..11), small programs with exponential / power cones and small
+with a box cone (problems.mpc_qp_box, seeds 0..11), small programs with exponential / power cones, with small PSD cones, and small
 second-order-cone programs (tests/problems.gen_feasible), each solved by scs.SCS(...).solve() with
 QDLDL and CPU_INDIRECT at eps 1e-4 (defaults) and 1e-9.
 """
@@ -37,7 +37,7 @@ def main():
     import scs
     from scs_python_b200 import problems as bp
     from tests import problems as tp
-    out = dict(source="scs.SCS(...).solve() of oracle/_ref (SCS 3.2.11), QDLDL and CPU_INDIRECT", mpc=[], soc=[], mpc_box=[], tri=[])
+    out = dict(source="scs.SCS(...).solve() of oracle/_ref (SCS 3.2.11), QDLDL and CPU_INDIRECT", mpc=[], soc=[], mpc_box=[], tri=[], psd=[])
     for seed in range(24):
         data, cone, _ = bp.mpc_qp(seed)
         rec = dict(seed=seed, runs={})
@@ -76,6 +76,19 @@ def main():
                 sol = scs.SCS(data, K, linear_solver=ls, verbose=False, eps_abs=eps, eps_rel=eps, max_iters=100000).solve()
                 rec["runs"]["%s_%g" % (name, eps)] = rec_of(sol)
         out["tri"].append(rec)
+    # small positive-semidefinite cones (one warp each in the batch kernel) next to the other cones
+    for seed, K, n, withP in [(21, dict(z=2, l=4, q=[3], s=[3, 5]), 14, True),
+                              (22, dict(z=0, l=3, s=[8], ep=2), 12, False),
+                              (23, dict(z=1, l=2, s=[1, 2, 4, 6], p=[0.4]), 16, True),
+                              (24, dict(z=3, l=0, s=[12]), 20, True),
+                              (25, dict(z=0, l=5, s=[16, 2]), 25, False)]:
+        data, p_star = tp.gen_feasible(K, n, 0.3, seed, with_P=withP)
+        rec = dict(seed=seed, cone=K, n=n, with_P=withP, p_star=p_star, runs={})
+        for eps in (1e-4, 1e-9):
+            for name, ls in (("qdldl", scs.LinearSolver.QDLDL), ("cpu_indirect", scs.LinearSolver.CPU_INDIRECT)):
+                sol = scs.SCS(data, K, linear_solver=ls, verbose=False, eps_abs=eps, eps_rel=eps, max_iters=100000).solve()
+                rec["runs"]["%s_%g" % (name, eps)] = rec_of(sol)
+        out["psd"].append(rec)
     json.dump(out, open(os.path.join(HERE, "batch_ref.json"), "w"), indent=0)
     its = [r["runs"]["cpu_indirect_0.0001"]["iter"] for r in out["mpc"]]
     print("batch_ref.json: %d mpc, %d soc; mpc iters at 1e-4 (indirect): min %d median %d max %d" %
