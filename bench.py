@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-time-to-eps", action="store_true")
     ap.add_argument("--no-batch", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     return ap.parse_args()
 
@@ -349,6 +350,45 @@ def batch_cfg5(scsb, rank, per_gpu=1024):
     return dict(problems=per_gpu, solved=solved, wall_s=wall, kernel_ms=st.get("kernel_ms"), admm_iters=iters)
 
 
+def other_configs(scsb):
+    """BASELINE.json configs[0], [2] and [3] on this GPU (N = 1 only): setup + solve to the default eps 1e-4 through the
+    public API with host buffers, the faster of two runs; next to each, the compiled reference's run of the same
+    seeded instance from tests/golden/full_ref.json (iterations and objective: the parity bar; its times were taken
+    in the build container, tools/bench_configs.py has the reference arms on the bench box)."""
+    from scs_python_b200 import problems as P
+    gold = {}
+    try:
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "full_ref.json")))
+    except Exception:
+        pass
+    res = {}
+    for name, gname, make in (("cfg1_cone_qp_n2000_m6000", "cfg1_qp", lambda: P.random_cone_qp(seed=1234, with_P=True)),
+                              ("cfg3_socp_portfolio_n50k_10k_cones", "cfg3_socp", lambda: P.socp_portfolio(seed=0)),
+                              ("cfg4_maxcut_sdp_64_psd200", "cfg4_sdp", lambda: P.maxcut_sdp(seed=0))):
+        try:
+            d, K, _ = make()
+            best = None
+            for _rep in range(2):
+                t = time.perf_counter()
+                sv = scsb.SCS(d, K, verbose=False)
+                i = sv.solve(warm_start=False)["info"]
+                wall = time.perf_counter() - t
+                sv._solver.finish()
+                del sv
+                rec = dict(status=i["status"], iters=i["iter"], wall_s=wall, setup_ms=i["setup_time"], solve_ms=i["solve_time"],
+                           iters_per_s=i["iter"] / max(i["solve_time"], 1e-9) * 1e3, pobj=i["pobj"], dobj=i["dobj"],
+                           res_pri=i["res_pri"], res_dual=i["res_dual"], gap=i["gap"])
+                if best is None or wall < best["wall_s"]:
+                    best = rec
+            g = gold.get(gname, {}).get("runs", {}).get("0.0001")
+            if g:
+                best["reference_fixture"] = dict(iters=g["iter"], pobj=g["pobj"], status=g["status"])
+            res[name] = best
+        except Exception as e:  # secondary keys never take the headline line down
+            res[name] = dict(error=repr(e))
+    return res
+
+
 def run_b200(args):
     rank, world, local, td = dist_setup()
     import scs_python_b200 as scsb
@@ -554,6 +594,8 @@ def run_b200(args):
         except Exception as e:  # a secondary key must never take the headline line down
             if rank == 0:
                 out["cfg5_batch_mpc"] = dict(error=repr(e))
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        out["other_configs"] = other_configs(scsb)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             out["cpu_baseline"] = cpu_baseline_sample(ips)
