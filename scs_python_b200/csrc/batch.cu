@@ -11,7 +11,7 @@
 //                        (linsys/cpu/indirect/private.c:50-316), CG tolerance rule scs.c:703-720
 //   tau root             root_plus (scs.c:667-688)
 //   cones                zero / nonneg inline, box cone by the CTA (Newton on t, cones.c:1174-1237), one warp per
-//                        second-order cone (cones.c:1242-1271), one thread per exponential / power cone (cone3.cuh), one warp per PSD cone (Jacobi, order <= 32),
+//                        second-order cone (cones.c:1242-1271), one thread per exponential / power cone (cone3.cuh), one warp per PSD / complex PSD cone (Jacobi, real order <= 32),
 //                        Moreau wrapper cones.c:1544-1588
 //   ADMM vector updates  scs.c:739-779
 //   residuals / stop     populate_residual_struct, has_converged, update_scale (scs.c:441-627, 1112-1189)
@@ -23,7 +23,7 @@
 // The grid is persistent: min(count, SMs x resident CTAs) CTAs pull problem indices from an atomic
 // counter, so uneven iteration counts do not leave SMs idle.  No host synchronisation happens
 // between the upload of the packed batch and the download of the solutions.
-// Problems the CTA cannot hold (shared-memory footprint, PSD cones of order > 32, complex PSD cones, warm
+// Problems the CTA cannot hold (shared-memory footprint, PSD cones of order > 32 / complex ones of order > 16, warm
 // start, time limit, AA relaxation != 1, lookback > 10) are solved by the streaming engine, one
 // after another -- still on the GPU, never on the host.
 #include <algorithm>
@@ -53,16 +53,17 @@ constexpr double kMaxScaleB = 1e6, kMinScaleB = 1e-6, kCgBestTolB = 1e-12, kCgTo
 constexpr double kMinNormB = 1e-4, kMaxNormB = 1e4;
 constexpr int kRuizB = 25, kL2B = 1;
 
-struct BDims { int n, m, nnzA, nnzP, nq, mem, direct, nb, np, tri, ds, pad; };  // maxima over the batch; direct: dense inverse resident; nb: box bounds
+struct BDims { int n, m, nnzA, nnzP, nq, mem, direct, nb, np, tri, ds, pslots; };  // maxima over the batch; direct: dense inverse resident; nb: box bounds
                                                                     // (bsize - 1); nq: cones with a boundary (SOC + exp + power); np: power cones;
-                                                                    // tri: some member has exp / power / PSD cones; ds: largest PSD order
+                                                                    // tri: some member has exp / power / PSD cones; ds: largest PSD order;
+                                                                    // pslots: warps that project PSD cones at a time (one workspace each)
 struct BStg {
   int normalize, adaptive_scale, max_iters, aa_mem, aa_interval, aa_type1, refine, pad;
   double scale, rho_x, eps_abs, eps_rel, eps_infeas, alpha, aa_reg;
 };
 struct BProb {
   int n, m, nnzA, nnzP, z, l, nq, bsize;  // bsize: box cone rows [t; s] right after the nonneg rows (cones.c:1174-1237)
-  int nsoc, ns, ep, ed, np, pad;          // nq = nsoc second-order cones, ns PSD cones (packed lower triangles), ep + ed exponential and
+  int nsoc, ns, ep, ed, np, ncs;          // nq = nsoc second-order cones, ns PSD + ncs complex PSD cones (packed), ep + ed exponential and
                                           // np power cones (3 rows each), in the reference's cone order (S/include/scs.h ScsCone)
   long long d_off, i_off, sol_off;
 };
@@ -95,7 +96,7 @@ struct BLay {
     aaR = take(d.mem > 0 ? d.mem * (2 * d.mem + 1) : 0);
     aaScr = take(d.mem > 0 ? 4 * d.mem * d.mem + 6 * d.mem + 8 : 0);
     bl = take(d.nb); bu = take(d.nb); pw = take(d.np);
-    psdw = take(d.ds > 0 ? kBW * psd_ws_doubles(d.ds) : 0);
+    psdw = take(d.ds > 0 ? d.pslots * psd_ws_doubles(d.ds) : 0);
     Ginv = take(d.direct ? d.n * (d.n | 1) : 0);
     nd = o;
     st_bytes = (int)((sizeof(AaState) + 15) / 16 * 16);
@@ -180,7 +181,7 @@ struct B {  // one CTA's view of its problem
   int n, m, l, nnzA, nnzP, z, nl, nq, tid;
   double *Aval, *AvalR, *Pval, *u, *ut, *v, *vp, *rsk, *g, *dr, *b, *c, *D, *E, *cp, *cr, *cGp, *cM, *tmp, *ws;
   double *aaR, *aaScr, *Ginv, *bl, *bu, *pw, *psdw;
-  int bsize, nsoc, ns, ep, ed, np, psd_ws;
+  int bsize, nsoc, ns, ncs, ep, ed, np, psd_ws;
   int direct, refine, gld, gparts, gshift;
   u16 *Arow, *Aperm, *Acol, *Acp, *Arp, *Pcol, *Prp, *qoff, *qlen;
   AaState *st;
@@ -703,33 +704,55 @@ __device__ __forceinline__ void soc_moreau_warp(double *uy, const double *ry, in
 }
 
 // One positive-semidefinite cone of the Moreau step, by one warp (cones.c:991-1148 inside cones.c:1562-1585; replaces
-// dsyevr + dsyrk for the small orders a batch member has).  x = -r s is unpacked (lower triangle, column-major,
-// off-diagonals scaled by sqrt 2) into a d x d matrix in shared memory; classical two-sided Jacobi with the
-// round-robin ordering -- the d/2 disjoint pairs of a round rotate together: angles from the current matrix, then the
-// column updates of all pairs (matrix and eigenvector matrix), then the row updates -- until a sweep finds no
-// off-diagonal entry above 1e-17 ||X||_F; X+ = sum_{lambda_k > 0} lambda_k v_k v_k' is re-packed and u = X+ / r + s.
-__device__ void psd_moreau_warp(double *uy, const double *ry, int len, double *ws, int lane) {
+// dsyevr + dsyrk / zheevr + zherk for the small orders a batch member has).  x = -r s is unpacked into a d x d
+// symmetric matrix in shared memory -- real cone: lower triangle, column-major, off-diagonals scaled by sqrt 2;
+// complex cone of order n (cones.c:1087-1095: per column the real diagonal entry, then (re, im) pairs): the real
+// embedding [[Re, -Im], [Im, Re]] of order d = 2n, whose projection is the embedding of the projection.  Classical
+// two-sided Jacobi with the round-robin ordering -- the d/2 disjoint pairs of a round rotate together: angles from the
+// current matrix, then the column updates of all pairs (matrix and eigenvector matrix), then the row updates --
+// until a sweep finds no off-diagonal entry above 1e-17 ||X||_F; X+ = sum_{lambda_k > 0} lambda_k v_k v_k' is
+// re-packed and u = X+ / r + s.
+struct PsdIdx { int i, j, part; };  // packed index -> entry (i >= j); part: 0 diagonal / real part, 1 imaginary part
+__device__ __forceinline__ PsdIdx psd_index(int k, int n, bool cplx) {
+  int j = 0, rem = k;
+  if (!cplx) {
+    while (rem >= n - j) { rem -= n - j; ++j; }
+    return PsdIdx{j + rem, j, 0};
+  }
+  while (rem >= 2 * (n - j) - 1) { rem -= 2 * (n - j) - 1; ++j; }
+  if (rem == 0) return PsdIdx{j, j, 0};
+  return PsdIdx{j + 1 + ((rem - 1) >> 1), j, (rem - 1) & 1};
+}
+__device__ void psd_moreau_warp(double *uy, const double *ry, int len, bool cplx, double *ws, int lane) {
   if (len <= 0) return;
-  const int d = (int)((sqrt(8.0 * len + 1.0) - 1.0) * 0.5 + 0.5);
-  if (d == 1) {
+  if (len == 1) {
     if (lane == 0) { const double s0 = uy[0], r0 = ry[0]; uy[0] = fmax(-r0 * s0, 0.0) / r0 + s0; }
     return;
   }
+  const int n = cplx ? (int)(sqrt((double)len) + 0.5) : (int)((sqrt(8.0 * len + 1.0) - 1.0) * 0.5 + 0.5);
+  const int d = cplx ? 2 * n : n;
   double *A = ws, *V = ws + d * d, *cs = V + d * d;
   const double isq2 = 0.70710678118654752440, sq2 = 1.41421356237309504880;
-  double fro = 0.0;
-  for (int k = lane; k < len; k += 32) {  // packed index k -> (i, j), i >= j
-    int j = 0, rem = k;
-    while (rem >= d - j) { rem -= d - j; ++j; }
-    const int i = j + rem;
-    const double x = -ry[k] * uy[k];
-    const double a = i == j ? x : x * isq2;
-    A[i * d + j] = a; A[j * d + i] = a;
-    fro = fma(i == j ? 1.0 : 2.0, a * a, fro);
-  }
-  for (int k = lane; k < d * d; k += 32) V[k] = (k / d == k % d) ? 1.0 : 0.0;
-  fro = sqrt(warp_sum(fro));
+  for (int k = lane; k < d * d; k += 32) { A[k] = 0.0; V[k] = (k / d == k % d) ? 1.0 : 0.0; }
   __syncwarp();
+  for (int k = lane; k < len; k += 32) {
+    const PsdIdx e = psd_index(k, n, cplx);
+    const double x = -ry[k] * uy[k];
+    const double a = e.i == e.j ? x : x * isq2;
+    if (!cplx) {
+      A[e.i * d + e.j] = a; A[e.j * d + e.i] = a;
+    } else if (e.part == 0) {
+      A[e.i * d + e.j] = a; A[e.j * d + e.i] = a;
+      A[(n + e.i) * d + n + e.j] = a; A[(n + e.j) * d + n + e.i] = a;
+    } else {  // Im H[i][j] = a, Im H[j][i] = -a: top-right block -Im H, bottom-left block Im H
+      A[e.i * d + n + e.j] = -a; A[(n + e.j) * d + e.i] = -a;
+      A[e.j * d + n + e.i] = a; A[(n + e.i) * d + e.j] = a;
+    }
+  }
+  __syncwarp();
+  double fro = 0.0;
+  for (int k = lane; k < d * d; k += 32) fro = fma(A[k], A[k], fro);
+  fro = sqrt(warp_sum(fro));
   const int de = d + (d & 1), half = de >> 1;
   const double small = 1e-17 * fro;
   for (int sweep = 0; sweep < 40; ++sweep) {
@@ -778,15 +801,14 @@ __device__ void psd_moreau_warp(double *uy, const double *ry, int len, double *w
     if (mx <= small) break;  // warp-uniform
   }
   for (int k = lane; k < len; k += 32) {
-    int j = 0, rem = k;
-    while (rem >= d - j) { rem -= d - j; ++j; }
-    const int i = j + rem;
+    const PsdIdx e = psd_index(k, n, cplx);
+    const int ra = e.part ? n + e.i : e.i, rb = e.j;  // Re H+[i][j] = S+[i][j], Im H+[i][j] = S+[n + i][j]
     double x = 0.0;
-    for (int e = 0; e < d; ++e) {
-      const double lam = A[e * d + e];
-      if (lam > 0.0) x = fma(lam * V[i * d + e], V[j * d + e], x);
+    for (int t = 0; t < d; ++t) {
+      const double lam = A[t * d + t];
+      if (lam > 0.0) x = fma(lam * V[ra * d + t], V[rb * d + t], x);
     }
-    if (i != j) x *= sq2;
+    if (e.i != e.j) x *= sq2;
     const double sk = uy[k];
     uy[k] = x / ry[k] + sk;
   }
@@ -859,7 +881,7 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
     const unsigned long long t_begin = gtimer();
     const BProb pb = a.probs[pid];
     s.n = pb.n; s.m = pb.m; s.l = pb.n + pb.m + 1; s.nnzA = pb.nnzA; s.nnzP = pb.nnzP;
-    s.z = pb.z; s.nl = pb.l; s.nq = pb.nq; s.bsize = pb.bsize; s.nsoc = pb.nsoc; s.ns = pb.ns; s.ep = pb.ep; s.ed = pb.ed; s.np = pb.np; s.cg_its = 0; s.gld = pb.n | 1;
+    s.z = pb.z; s.nl = pb.l; s.nq = pb.nq; s.bsize = pb.bsize; s.nsoc = pb.nsoc; s.ns = pb.ns; s.ncs = pb.ncs; s.ep = pb.ep; s.ed = pb.ed; s.np = pb.np; s.cg_its = 0; s.gld = pb.n | 1;
     s.gshift = 0;
     while (s.gshift < 5 && (pb.n << (s.gshift + 1)) <= kBT) ++s.gshift;  // lanes per output of ginv_apply
     s.gparts = 1 << s.gshift;
@@ -1017,10 +1039,12 @@ __global__ void __launch_bounds__(kBT, kBCtasPerSm) k_batch_solve(const BArgs a)
         for (int cidx = warp; cidx < s.nsoc; cidx += kBW)
           soc_moreau_warp(s.u + n + s.qoff[cidx], s.dr + n + s.qoff[cidx], s.qlen[cidx], lane);
         if (kTri) {  // PSD cones: one warp each; exponential / power cones: one thread each (x = -R s, project, x / r + s)
-          for (int cidx = s.nsoc + warp; cidx < s.nsoc + s.ns; cidx += kBW)
-            psd_moreau_warp(s.u + n + s.qoff[cidx], s.dr + n + s.qoff[cidx], s.qlen[cidx], s.psdw + warp * s.psd_ws, lane);
-          for (int cidx = s.nsoc + s.ns + s.tid; cidx < s.nq; cidx += kBT) {
-            const int t3 = cidx - s.nsoc - s.ns;
+          if (warp < a.dims.pslots)
+            for (int cidx = s.nsoc + warp; cidx < s.nsoc + s.ns + s.ncs; cidx += a.dims.pslots)
+              psd_moreau_warp(s.u + n + s.qoff[cidx], s.dr + n + s.qoff[cidx], s.qlen[cidx], cidx >= s.nsoc + s.ns,
+                              s.psdw + warp * s.psd_ws, lane);
+          for (int cidx = s.nsoc + s.ns + s.ncs + s.tid; cidx < s.nq; cidx += kBT) {
+            const int t3 = cidx - s.nsoc - s.ns - s.ncs;
             double *uy = s.u + n + s.qoff[cidx];
             const double *ry = s.dr + n + s.qoff[cidx];
             const double s0 = uy[0], s1 = uy[1], s2 = uy[2];
@@ -1149,8 +1173,11 @@ static Eligibility fused_eligible(const ScsData *d, const ScsCone *k, const ScsS
   if (stgs->warm_start || stgs->time_limit_secs > 0) return e;
   if (stgs->acceleration_lookback > kBAaMax) return e;
   if (stgs->acceleration_lookback > 0 && stgs->acceleration_relaxation != 1.0) return e;
-  if (k->cssize > 0) return e;
   long long ncones = 0;
+  for (int i = 0; i < k->cssize; ++i) {  // complex cones go through the real embedding of order 2 cs
+    if (k->cs[i] < 1 || 2 * k->cs[i] > kBPsdMax) return e;
+    e.ds = std::max(e.ds, 2 * (int)k->cs[i]);
+  }
   for (int i = 0; i < k->ssize; ++i) {
     if (k->s[i] < 1 || k->s[i] > kBPsdMax) return e;
     e.ds = std::max(e.ds, (int)k->s[i]);
@@ -1166,7 +1193,7 @@ static Eligibility fused_eligible(const ScsData *d, const ScsCone *k, const ScsS
   if (d->n >= 65535 || d->m >= 65535 || nnzA >= 65535 || nnzP >= 65535) return e;
   e.nnzP_full = (int)nnzP;
   e.n3 = (int)(k->ep + k->ed + k->psize);
-  ncones = (long long)k->qsize + k->ssize + e.n3;
+  ncones = (long long)k->qsize + k->ssize + k->cssize + e.n3;
   if (ncones >= 65535) return e;
   e.nq = (int)ncones;
   e.ok = true;
@@ -1275,6 +1302,8 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
     t.tri = t.tri || elig[i].n3 > 0 || elig[i].ds > 0;
     t.ds = std::max(t.ds, elig[i].ds);
     t.mem = std::min((int)stgs->acceleration_lookback, kBAaMax);
+    t.pslots = t.ds > 0 ? kBW : 0;  // as many PSD workspaces (one per warp) as the footprint allows
+    while (t.pslots > 1 && BLay(t).bytes() > 200 * 1024) t.pslots >>= 1;
     if (BLay(t).bytes() > 200 * 1024) { elig[i].ok = false; continue; }  // would not fit next to the others
     dims = t;
     fused.push_back(i);
@@ -1298,8 +1327,8 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
       BProb &p = probs[f];
       p.n = dd->n; p.m = dd->m; p.nnzA = dd->A->p[dd->n]; p.nnzP = elig[fused[f]].nnzP_full;
       p.z = kk->z; p.l = kk->l; p.bsize = kk->bsize;
-      p.nsoc = kk->qsize; p.ns = kk->ssize; p.ep = kk->ep; p.ed = kk->ed; p.np = kk->psize; p.pad = 0;
-      p.nq = p.nsoc + p.ns + p.ep + p.ed + p.np;
+      p.nsoc = kk->qsize; p.ns = kk->ssize; p.ncs = kk->cssize; p.ep = kk->ep; p.ed = kk->ed; p.np = kk->psize;
+      p.nq = p.nsoc + p.ns + p.ncs + p.ep + p.ed + p.np;
       p.d_off = dtot; p.i_off = itot; p.sol_off = stot;
       dtot += dpool_count(p.n, p.m, p.nnzA, p.nnzP, p.bsize > 1 ? p.bsize - 1 : 0, p.np);
       itot += ipool_count(p.n, p.m, p.nnzA, p.nnzP, p.nq);
@@ -1372,7 +1401,8 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
       int off = kk->z + kk->l + kk->bsize;
       for (int c = 0; c < p.nsoc; ++c) { qoff[c] = (u16)off; qlen[c] = (u16)kk->q[c]; off += kk->q[c]; }
       for (int c = 0; c < p.ns; ++c) { const int len = kk->s[c] * (kk->s[c] + 1) / 2; qoff[p.nsoc + c] = (u16)off; qlen[p.nsoc + c] = (u16)len; off += len; }
-      for (int c = p.nsoc + p.ns; c < p.nq; ++c) { qoff[c] = (u16)off; qlen[c] = 3; off += 3; }  // ep, ed, power cones (reference order; complex PSD members take the streaming engine)
+      for (int c = 0; c < p.ncs; ++c) { const int len = kk->cs[c] * kk->cs[c]; qoff[p.nsoc + p.ns + c] = (u16)off; qlen[p.nsoc + p.ns + c] = (u16)len; off += len; }
+      for (int c = p.nsoc + p.ns + p.ncs; c < p.nq; ++c) { qoff[c] = (u16)off; qlen[c] = 3; off += 3; }  // ep, ed, power cones (reference order)
     }
     const double pack_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
     // ---- device

@@ -37,7 +37,7 @@ def main():
     import scs
     from scs_python_b200 import problems as bp
     from tests import problems as tp
-    out = dict(source="scs.SCS(...).solve() of oracle/_ref (SCS 3.2.11), QDLDL and CPU_INDIRECT", mpc=[], soc=[], mpc_box=[], tri=[], psd=[])
+    out = dict(source="scs.SCS(...).solve() of oracle/_ref (SCS 3.2.11), QDLDL and CPU_INDIRECT", mpc=[], soc=[], mpc_box=[], tri=[], psd=[], cpsd=[])
     for seed in range(24):
         data, cone, _ = bp.mpc_qp(seed)
         rec = dict(seed=seed, runs={})
@@ -89,6 +89,18 @@ def main():
                 sol = scs.SCS(data, K, linear_solver=ls, verbose=False, eps_abs=eps, eps_rel=eps, max_iters=100000).solve()
                 rec["runs"]["%s_%g" % (name, eps)] = rec_of(sol)
         out["psd"].append(rec)
+    # complex positive-semidefinite cones (real embedding of order 2 cs in the batch kernel)
+    for seed, K, n, withP in [(41, dict(z=2, l=3, cs=[3]), 12, True),
+                              (42, dict(z=0, l=4, q=[3], s=[3], cs=[2, 5], ep=1), 18, False),
+                              (43, dict(z=1, l=2, cs=[1, 8]), 20, True),
+                              (44, dict(z=0, l=3, cs=[16]), 30, False)]:
+        data, p_star = tp.gen_feasible(K, n, 0.3, seed, with_P=withP)
+        rec = dict(seed=seed, cone=K, n=n, with_P=withP, p_star=p_star, runs={})
+        for eps in (1e-4, 1e-9):
+            for name, ls in (("qdldl", scs.LinearSolver.QDLDL), ("cpu_indirect", scs.LinearSolver.CPU_INDIRECT)):
+                sol = scs.SCS(data, K, linear_solver=ls, verbose=False, eps_abs=eps, eps_rel=eps, max_iters=100000).solve()
+                rec["runs"]["%s_%g" % (name, eps)] = rec_of(sol)
+        out["cpsd"].append(rec)
     json.dump(out, open(os.path.join(HERE, "batch_ref.json"), "w"), indent=0)
     its = [r["runs"]["cpu_indirect_0.0001"]["iter"] for r in out["mpc"]]
     print("batch_ref.json: %d mpc, %d soc; mpc iters at 1e-4 (indirect): min %d median %d max %d" %

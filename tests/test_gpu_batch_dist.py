@@ -138,15 +138,16 @@ def test_batch_exp_and_power_cones_vs_reference_golden(scsb, eps):
         assert _rel(a["info"]["pobj"], b["info"]["pobj"]) < tol
 
 
+@pytest.mark.parametrize("section", ["psd", "cpsd"])
 @pytest.mark.parametrize("eps", [1e-9, 1e-4])
-def test_batch_small_psd_cones_vs_reference_golden(scsb, eps):
+def test_batch_small_psd_cones_vs_reference_golden(scsb, eps, section):
     """Positive-semidefinite cones of order 1..16 inside the one-CTA kernel (one warp per cone, two-sided Jacobi in
-    shared memory; cones.c:991-1148): every member on the fused path; status, objectives and iteration counts against
+    shared memory; cones.c:991-1148) and complex ones of order 1..16 through their real embedding: every member on the fused path; status, objectives and iteration counts against
     the compiled reference's QDLDL runs (which project with LAPACK dsyevr), host-side residual / cone checks, and
     the same members through the streaming engine (blocked one-sided Jacobi kernels of cones.cu)."""
     from scs_python_b200 import _scs_b200 as B
     probs = []
-    for g in GOLD["psd"]:
+    for g in GOLD[section]:
         d, _ = tp.gen_feasible(g["cone"], g["n"], 0.3, g["seed"], with_P=bool(g["with_P"]))
         probs.append((d, g["cone"]))
     sols = scsb.solve_batch(probs, eps_abs=eps, eps_rel=eps, max_iters=100000, verbose=False)
@@ -154,21 +155,21 @@ def test_batch_small_psd_cones_vs_reference_golden(scsb, eps):
     assert st["fused"] == len(probs) and st["streamed"] == 0, st
     tol = 1e-6 if eps < 1e-8 else 2e-3
     its, ref = [], []
-    for s, g, (d, k) in zip(sols, GOLD["psd"], probs):
+    for s, g, (d, k) in zip(sols, GOLD[section], probs):
         r = g["runs"]["qdldl_%g" % eps]
         assert s["info"]["status_val"] == r["status_val"] == 1, (g["seed"], s["info"]["status"], r["status"])
         assert _rel(s["info"]["pobj"], r["pobj"]) < tol, (g["seed"], s["info"]["pobj"], r["pobj"])
         assert _rel(s["info"]["dobj"], r["dobj"]) < tol, (g["seed"], s["info"]["dobj"], r["dobj"])
         helpers.verify_solution(d, k, s, max(eps, 1e-8), max(eps, 1e-8))
         its.append(s["info"]["iter"]); ref.append(r["iter"])
-    print("PSD batch members, eps %g: iterations b200 %s / reference QDLDL %s" % (eps, its, ref))
+    print(section + " batch members, eps %g: iterations b200 %s / reference QDLDL %s" % (eps, its, ref))
     if eps == 1e-9:
         assert np.all(np.abs(np.array(its) - np.array(ref)) <= 50), (its, ref)
     for (d, k), s in list(zip(probs, sols))[:2]:
         a = scsb.SCS(d, k, eps_abs=eps, eps_rel=eps, max_iters=100000, verbose=False).solve(warm_start=False)
         assert a["info"]["status_val"] == 1 and _rel(a["info"]["pobj"], s["info"]["pobj"]) < tol
-    # a PSD cone above the in-kernel order limit (32) sends its member to the streaming engine, the rest stay fused
-    K = dict(z=1, l=2, s=[34])
+    # a cone above the in-kernel order limit (real 32, complex 16) sends its member to the streaming engine, the rest stay fused
+    K = dict(z=1, l=2, s=[34]) if section == "psd" else dict(z=1, l=2, cs=[17])
     d, _ = tp.gen_feasible(K, 12, 0.3, 31, with_P=False)
     ms = scsb.solve_batch([probs[0], (d, K)], eps_abs=1e-6, eps_rel=1e-6, max_iters=100000, verbose=False)
     st = B.batch_stats()
