@@ -332,7 +332,8 @@ scs_int scs_b200_dist_world(void);
 /* Solve `count` independent problems on the current device (no reference counterpart: the
  * reference API is single-problem; BASELINE.json configs[4]).  Arrays of pointers,
  * one per problem; `sol[i]` vectors are allocated when NULL, exactly as scs_solve does.  Problems
- * that fit (zero / nonneg / second-order cones, shared-memory footprint <= 200 KB, cold start,
+ * that fit (every cone of the default build -- zero, nonneg, box, second-order, PSD up to order 32, complex PSD up
+ * to order 16, exponential, power; shared-memory footprint <= 200 KB, cold start,
  * lookback <= 10) are solved by the batch engine: ONE kernel launch, one CTA per problem with all
  * state in shared memory (csrc/batch.cu); the others go through the streaming engine one after
  * another.  Batch sharding across GPUs is done by the caller: one process per GPU, problem
@@ -340,6 +341,12 @@ scs_int scs_b200_dist_world(void);
 scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, const ScsCone *const *k,
                              const ScsSettings *stgs, ScsSolution *const *sol, ScsInfo *info,
                              scs_int streams);
+/* Host-only: the plan scs_b200_solve_batch would make (no device is touched).  fused_out[count]: 1 = batch kernel,
+ * 0 = streaming engine, -1 = fails validation; dims_out[8] = {shared-memory bytes per CTA, resident dense inverse,
+ * kernel instantiation with exp / power / PSD cones, largest PSD order (complex: 2 cs), PSD workspaces, cones with a
+ * boundary, power cones, box bounds}.  Returns the number of members the batch kernel takes, or -1. */
+scs_int scs_b200_batch_plan(scs_int count, const ScsData *const *d, const ScsCone *const *k, const ScsSettings *stgs,
+                            scs_int *fused_out, scs_int *dims_out);
 /* how the last scs_b200_solve_batch of this process ran: out = {problems in the batch engine,
  * problems streamed, batch-kernel ms (CUDA events), host packing ms, H2D bytes, D2H bytes,
  * CTAs launched, shared memory per CTA, 1 if the batch kernel ran in direct mode (resident dense

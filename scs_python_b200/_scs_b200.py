@@ -189,6 +189,9 @@ lib.scs_b200_solve_batch.restype = c_int
 lib.scs_b200_solve_batch.argtypes = [c_int, C.POINTER(C.POINTER(ScsData)), C.POINTER(C.POINTER(ScsCone)),
                                      C.POINTER(ScsSettings), C.POINTER(C.POINTER(ScsSolution)),
                                      C.POINTER(ScsInfo), c_int]
+lib.scs_b200_batch_plan.restype = c_int
+lib.scs_b200_batch_plan.argtypes = [c_int, C.POINTER(C.POINTER(ScsData)), C.POINTER(C.POINTER(ScsCone)), C.POINTER(ScsSettings),
+                                    C.POINTER(c_int), C.POINTER(c_int)]
 lib.scs_b200_batch_stats.restype = c_int
 lib.scs_b200_batch_stats.argtypes = [C.POINTER(c_double * 18)]
 
@@ -578,22 +581,15 @@ def _i32(a, name):
     return _check_int_1d(a, name)
 
 
-def solve_batch(problems, **settings):
-    """Solve independent problems in one call (include/scs_b200.h: scs_b200_solve_batch).
-
-    problems: sequence of (shape, Ax, Ai, Ap, Px, Pi, Pp, b, c, cone) tuples -- the constructor
-    arguments of `SCS` -- all solved with the same settings.  Returns a list of
-    {"x","y","s","info"} dicts in input order.  The argument checks are those of `SCS`; the C structures
-    of the whole batch are filled in place in five contiguous arrays."""
+def _fill_batch(problems):
+    """C structures of a batch, filled in place in contiguous arrays (shared by solve_batch and batch_plan)."""
     cnt = len(problems)
-    stgs, keep_stgs = make_settings(settings)
     nalloc = max(cnt, 1)
     matsA, matsP = (_MatA * nalloc)(), (_MatA * nalloc)()
-    datas, cones, sols = (_DataA * nalloc)(), (_ConeA * nalloc)(), (_SolA * nalloc)()
-    infos = (ScsInfo * nalloc)()
+    datas, cones = (_DataA * nalloc)(), (_ConeA * nalloc)()
     szM = C.sizeof(_MatA)
     baseA, baseP = C.addressof(matsA), C.addressof(matsP)
-    keep = []
+    keep = [matsA, matsP]
     dims = []
     for idx, (shape, Ax, Ai, Ap, Px, Pi, Pp, b, c, cone) in enumerate(problems):
         m, n = int(shape[0]), int(shape[1])
@@ -632,6 +628,47 @@ def solve_batch(problems, **settings):
             C.memmove(C.addressof(k), C.addressof(ks), C.sizeof(ScsCone))
             keep.append((Ax, Ai, Ap, Px, Pi, Pp, b, c, ks, keep_cone))
         dims.append((n, m))
+    return nalloc, datas, cones, keep, dims
+
+
+def _ptr_array(arr, size, typ, nalloc):
+    pa = (C.c_void_p * nalloc)()
+    np.frombuffer(pa, dtype=np.uint64)[:] = C.addressof(arr) + size * np.arange(nalloc, dtype=np.uint64)
+    return pa, C.cast(pa, C.POINTER(C.POINTER(typ)))
+
+
+def batch_plan(problems, **settings):
+    """Host-only (include/scs_b200.h: scs_b200_batch_plan): which members of the batch the one-CTA kernel takes and
+    the shared-memory carve-up they share.  Returns (fused, plan): fused[i] = 1 batch kernel / 0 streaming engine /
+    -1 fails validation; plan = dict(smem_bytes, direct, extended_cones, psd_order, psd_workspaces, cones, power_cones,
+    box_bounds).  No device is touched."""
+    cnt = len(problems)
+    stgs, keep_stgs = make_settings(settings)
+    nalloc, datas, cones, keep, _ = _fill_batch(problems)
+    pd, pdc = _ptr_array(datas, C.sizeof(_DataA), ScsData, nalloc)
+    pk, pkc = _ptr_array(cones, C.sizeof(_ConeA), ScsCone, nalloc)
+    fused = (c_int * nalloc)()
+    out = (c_int * 8)()
+    rc = lib.scs_b200_batch_plan(cnt, pdc, pkc, C.byref(stgs), fused, out)
+    del keep_stgs, keep, pd, pk
+    if rc < 0:
+        raise ValueError("scs_b200_batch_plan failed")
+    names = ("smem_bytes", "direct", "extended_cones", "psd_order", "psd_workspaces", "cones", "power_cones", "box_bounds")
+    return [int(fused[i]) for i in range(cnt)], dict(zip(names, (int(v) for v in out)))
+
+
+def solve_batch(problems, **settings):
+    """Solve independent problems in one call (include/scs_b200.h: scs_b200_solve_batch).
+
+    problems: sequence of (shape, Ax, Ai, Ap, Px, Pi, Pp, b, c, cone) tuples -- the constructor
+    arguments of `SCS` -- all solved with the same settings.  Returns a list of
+    {"x","y","s","info"} dicts in input order.  The argument checks are those of `SCS`; the C structures
+    of the whole batch are filled in place in five contiguous arrays."""
+    cnt = len(problems)
+    stgs, keep_stgs = make_settings(settings)
+    nalloc, datas, cones, keep, dims = _fill_batch(problems)
+    sols = (_SolA * nalloc)()
+    infos = (ScsInfo * nalloc)()
     # one output block for the whole batch: x | y | s per problem
     offs = np.zeros(cnt + 1, dtype=np.int64)
     if cnt:
@@ -645,13 +682,9 @@ def solve_batch(problems, **settings):
         sl.x, sl.y, sl.s = base + 8 * o, base + 8 * (o + n), base + 8 * (o + n + m)
         out.append((block[o:o + n], block[o + n:o + n + m], block[o + n + m:o + n + 2 * m]))
 
-    def ptr_array(arr, size, typ):
-        pa = (C.c_void_p * nalloc)()
-        np.frombuffer(pa, dtype=np.uint64)[:] = C.addressof(arr) + size * np.arange(nalloc, dtype=np.uint64)
-        return pa, C.cast(pa, C.POINTER(C.POINTER(typ)))
-    pd, pdc = ptr_array(datas, C.sizeof(_DataA), ScsData)
-    pk, pkc = ptr_array(cones, C.sizeof(_ConeA), ScsCone)
-    ps, psc = ptr_array(sols, C.sizeof(_SolA), ScsSolution)
+    pd, pdc = _ptr_array(datas, C.sizeof(_DataA), ScsData, nalloc)
+    pk, pkc = _ptr_array(cones, C.sizeof(_ConeA), ScsCone, nalloc)
+    ps, psc = _ptr_array(sols, C.sizeof(_SolA), ScsSolution, nalloc)
     lib.scs_b200_solve_batch(cnt, pdc, pkc, C.byref(stgs), psc, infos, 0)  # ctypes releases the GIL
     del keep_stgs, keep, pd, pk, ps
     return [{"x": x, "y": y, "s": s, "info": _info_dict(infos[i])} for i, (x, y, s) in enumerate(out)]

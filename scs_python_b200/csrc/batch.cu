@@ -1200,6 +1200,44 @@ static Eligibility fused_eligible(const ScsData *d, const ScsCone *k, const ScsS
   return e;
 }
 
+// Host plan of a batch (no device work): which members the one-CTA kernel takes, and the shared-memory carve-up
+// (maxima over those members) they share.  A member that fails validation is marked nq = -1.
+static void batch_classify(int count, const ScsData *const *d, const ScsCone *const *k, const ScsSettings *stgs,
+                           std::vector<Eligibility> &elig, std::vector<int> &fused, BDims &dims) {
+  elig.assign((size_t)count, Eligibility{false, 0, 0, 0, 0});
+  fused.clear();
+  dims = BDims{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < count; ++i) {
+    if (!d[i] || !k[i] || validate_problem(d[i], k[i], stgs) < 0) {
+      elig[i].nq = -1;
+      continue;
+    }
+    elig[i] = fused_eligible(d[i], k[i], stgs);
+    if (!elig[i].ok) continue;
+    BDims t = dims;
+    t.n = std::max(t.n, (int)d[i]->n); t.m = std::max(t.m, (int)d[i]->m);
+    t.nnzA = std::max(t.nnzA, (int)d[i]->A->p[d[i]->n]); t.nnzP = std::max(t.nnzP, elig[i].nnzP_full);
+    t.nq = std::max(t.nq, elig[i].nq);
+    t.nb = std::max(t.nb, k[i]->bsize > 1 ? (int)k[i]->bsize - 1 : 0);
+    t.np = std::max(t.np, (int)k[i]->psize);
+    t.tri = t.tri || elig[i].n3 > 0 || elig[i].ds > 0;
+    t.ds = std::max(t.ds, elig[i].ds);
+    t.mem = std::min((int)stgs->acceleration_lookback, kBAaMax);
+    t.pslots = t.ds > 0 ? kBW : 0;  // as many PSD workspaces (one per warp) as the footprint allows
+    while (t.pslots > 1 && BLay(t).bytes() > 200 * 1024) t.pslots >>= 1;
+    if (BLay(t).bytes() > 200 * 1024) { elig[i].ok = false; continue; }  // would not fit next to the others
+    dims = t;
+    fused.push_back(i);
+  }
+}
+// linear-system mode of the batch kernel: resident dense inverse when it fits, PCG otherwise
+static void batch_pick_linsys(BDims &dims, bool any) {
+  const char *e = getenv("SCS_B200_BATCH_DIRECT");
+  BDims t = dims;
+  t.direct = 1;
+  if (!(e && atoi(e) == 0) && any && BLay(t).bytes() <= 227 * 1024) dims.direct = 1;
+}
+
 static void status_string(int status_val, int iter, int max_iters, char *out) {
   const char *base = "failure";
   switch (status_val) {
@@ -1270,6 +1308,24 @@ static BatchStats g_last_batch;
 
 using namespace b200;
 
+// Host-only: the plan scs_b200_solve_batch would make for this batch.  fused_out[count]: 1 = one-CTA kernel, 0 =
+// streaming engine, -1 = fails validation; dims_out[8] = {shared-memory bytes per CTA, resident dense inverse (0/1),
+// kernel instantiation with exp / power / PSD cones (0/1), largest PSD order (complex: 2 cs), PSD workspaces,
+// cones with a boundary, power cones, box bounds}.  No device is touched (tests of the host logic).
+extern "C" scs_int scs_b200_batch_plan(scs_int count, const ScsData *const *d, const ScsCone *const *k,
+                                       const ScsSettings *stgs, scs_int *fused_out, scs_int *dims_out) {
+  if (count < 0 || !d || !k || !stgs || !fused_out || !dims_out) return -1;
+  std::vector<int> fused;
+  std::vector<Eligibility> elig;
+  BDims dims;
+  batch_classify((int)count, d, k, stgs, elig, fused, dims);
+  batch_pick_linsys(dims, !fused.empty());
+  for (int i = 0; i < count; ++i) fused_out[i] = elig[i].nq == -1 ? -1 : (elig[i].ok ? 1 : 0);
+  dims_out[0] = fused.empty() ? 0 : (scs_int)BLay(dims).bytes(); dims_out[1] = dims.direct; dims_out[2] = dims.tri;
+  dims_out[3] = dims.ds; dims_out[4] = dims.pslots; dims_out[5] = dims.nq; dims_out[6] = dims.np; dims_out[7] = dims.nb;
+  return (scs_int)fused.size();
+}
+
 extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, const ScsCone *const *k,
                                         const ScsSettings *stgs, ScsSolution *const *sol, ScsInfo *info,
                                         scs_int streams) {
@@ -1281,41 +1337,21 @@ extern "C" scs_int scs_b200_solve_batch(scs_int count, const ScsData *const *d, 
   scs_int worst = 0;
   // ---- classify
   std::vector<int> fused;
-  std::vector<Eligibility> elig((size_t)count);
-  BDims dims{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<Eligibility> elig;
+  BDims dims;
+  batch_classify((int)count, d, k, stgs, elig, fused, dims);
   for (int i = 0; i < count; ++i) {
-    if (!d[i] || !k[i] || !sol[i] || validate_problem(d[i], k[i], stgs) < 0) {
+    if (elig[i].nq == -1 || !sol[i]) {  // failed validation
       populate_on_failure(d[i] ? d[i]->m : -1, d[i] ? d[i]->n : -1, sol[i], &info[i], SCS_FAILED, "failure");
       worst = SCS_FAILED;
+      if (elig[i].ok) fused.erase(std::remove(fused.begin(), fused.end(), i), fused.end());
       elig[i].ok = false;
-      elig[i].nq = -1;  // marks "already failed"
-      continue;
+      elig[i].nq = -1;
     }
-    elig[i] = fused_eligible(d[i], k[i], stgs);
-    if (!elig[i].ok) continue;
-    BDims t = dims;
-    t.n = std::max(t.n, (int)d[i]->n); t.m = std::max(t.m, (int)d[i]->m);
-    t.nnzA = std::max(t.nnzA, (int)d[i]->A->p[d[i]->n]); t.nnzP = std::max(t.nnzP, elig[i].nnzP_full);
-    t.nq = std::max(t.nq, elig[i].nq);
-    t.nb = std::max(t.nb, k[i]->bsize > 1 ? (int)k[i]->bsize - 1 : 0);
-    t.np = std::max(t.np, (int)k[i]->psize);
-    t.tri = t.tri || elig[i].n3 > 0 || elig[i].ds > 0;
-    t.ds = std::max(t.ds, elig[i].ds);
-    t.mem = std::min((int)stgs->acceleration_lookback, kBAaMax);
-    t.pslots = t.ds > 0 ? kBW : 0;  // as many PSD workspaces (one per warp) as the footprint allows
-    while (t.pslots > 1 && BLay(t).bytes() > 200 * 1024) t.pslots >>= 1;
-    if (BLay(t).bytes() > 200 * 1024) { elig[i].ok = false; continue; }  // would not fit next to the others
-    dims = t;
-    fused.push_back(i);
   }
   const int dev = current_device();
   if (cudaSetDevice(dev) != cudaSuccess) return -1;
-  {  // linear-system mode of the batch kernel: resident dense inverse when it fits, PCG otherwise
-    const char *e = getenv("SCS_B200_BATCH_DIRECT");
-    BDims t = dims;
-    t.direct = 1;
-    if (!(e && atoi(e) == 0) && !fused.empty() && BLay(t).bytes() <= 227 * 1024) dims.direct = 1;
-  }
+  batch_pick_linsys(dims, !fused.empty());
   // ---- fused path
   if (!fused.empty()) {
     const int nf = (int)fused.size();

@@ -375,3 +375,45 @@ def test_column_classification_reassembles_the_problem(world, kind):
     assert abs(sp.csc_matrix(Afull) - A).sum() == 0
     if world > 1 and kind == "lasso":  # the y block of LASSO (identity columns) is private: less than half is shared
         assert len(shared) < 0.6 * n
+
+
+def test_batch_plan_eligibility_and_footprint():
+    """scs_b200_batch_plan (host only): which members the one-CTA batch kernel takes.  Every cone of the default
+    build is eligible (PSD up to order 32, complex PSD up to 16); warm starts, time limits, lookback > 10 and
+    oversized footprints go to the streaming engine; invalid members are reported, not planned; the shared
+    carve-up is the maximum over the members and the PSD workspaces shrink before a member is turned away."""
+    import scs_python_b200 as scsb
+    from scs_python_b200 import _scs_b200 as B, problems as P
+    from tests import problems as tp
+    prep = lambda d, k: scsb._prepare(d, k)
+    mpc, box = prep(*P.mpc_qp(0)[:2]), prep(*P.mpc_qp_box(1)[:2])
+    fused, plan = B.batch_plan([mpc, box], verbose=False)
+    assert fused == [1, 1] and plan["direct"] == 1 and plan["extended_cones"] == 0 and plan["box_bounds"] == 120
+    assert 0 < plan["smem_bytes"] <= 227 * 1024
+    mk = lambda K, n=12, seed=31: prep(tp.gen_feasible(K, n, 0.3, seed, with_P=False)[0], K)
+    for K, want in ((dict(z=1, l=2, s=[32]), 1), (dict(z=1, l=2, s=[33]), 0), (dict(z=1, l=2, cs=[16]), 1),
+                    (dict(z=1, l=2, cs=[17]), 0), (dict(z=1, l=4, ep=2, ed=2, p=[-0.4, 0.7]), 1),
+                    (dict(z=2, l=4, q=[3], s=[3, 5], cs=[2]), 1)):
+        f, pl = B.batch_plan([mk(K)], verbose=False)
+        assert f == [want], (K, f, pl)
+        if want:
+            assert pl["extended_cones"] == 1
+            assert pl["psd_order"] == max([0] + list(K.get("s", [])) + [2 * c for c in K.get("cs", [])])
+    # settings the kernel does not implement
+    for kw in (dict(time_limit_secs=1.0), dict(acceleration_lookback=11),
+               dict(acceleration_lookback=5, acceleration_relaxation=1.5)):
+        assert B.batch_plan([mpc], verbose=False, **kw)[0] == [0], kw
+    # a large member keeps its place by giving up PSD workspaces: order-32 embedding next to a 2.3 k-entry matrix
+    K = dict(z=0, l=3, cs=[16])
+    big = prep(tp.gen_feasible(K, 30, 0.3, 44, with_P=False)[0], K)
+    f, pl = B.batch_plan([big], verbose=False)
+    assert f == [1] and 1 <= pl["psd_workspaces"] < 8 and pl["smem_bytes"] <= 200 * 1024, pl
+    # mixed batch: maxima over the members; the oversized PSD member alone is turned away
+    f, pl = B.batch_plan([mpc, mk(dict(z=1, l=2, s=[33])), mk(dict(z=1, l=2, s=[6])), box], verbose=False)
+    assert f == [1, 0, 1, 1] and pl["psd_order"] == 6 and pl["box_bounds"] == 120
+    # a member whose cone sizes do not add up to m fails validation (reported as -1), the rest is planned
+    bad = list(mk(dict(z=1, l=2, q=[3])))
+    bad[-1] = dict(z=1, l=2, q=[4])
+    f, pl = B.batch_plan([mpc, tuple(bad)], verbose=False)
+    assert f == [1, -1]
+    assert B.batch_plan([], verbose=False)[0] == []
