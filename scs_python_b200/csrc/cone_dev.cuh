@@ -1,12 +1,155 @@
-// cone3.cuh -- projections onto the three-dimensional cones (exponential, power), one thread per cone.
-// Device functions shared by the streaming engine (cones.cu: k_exp_cones / k_pow_cones) and the batch engine
-// (batch.cu).  Scalar root finders whose constants and branch order follow the reference (S/src/exp_cone.c,
-// S/src/cones.c:1276-1324) because parity with its iterates depends on them.
+// cone_dev.cuh -- cone projections that run inside another kernel: per-thread and per-warp device functions shared
+// by the streaming engine (cones.cu: k_exp_cones / k_pow_cones) and the one-CTA batch engine (batch.cu).
+//
+//   second-order cone        one warp, shuffle-reduced norm (cones.c:1242-1271), Moreau step fused
+//   PSD / complex PSD cone   one warp, two-sided Jacobi with round-robin ordering on a matrix in shared memory
+//                            (replaces dsyevr + dsyrk / zheevr + zherk, cones.c:991-1148, for small orders)
+//   exponential / power      one thread per three-row cone: scalar root finders whose constants and branch order
+//                            follow the reference (S/src/exp_cone.c, S/src/cones.c:1276-1324) because parity with
+//                            its iterates depends on them
 #pragma once
 #include "common.cuh"
 
 namespace b200 {
 namespace {
+
+// =========================================================== second-order / PSD, one warp per cone ======
+// one second-order cone of the Moreau step, by one warp (cones.c:1242-1271 inside cones.c:1562-1585)
+__device__ __forceinline__ void soc_moreau_warp(double *uy, const double *ry, int len, int lane) {
+  if (len <= 0) return;
+  // x = -r s ; u = Pi_K(x) / r + s
+  double nn = 0.0;
+  for (int k = 1 + lane; k < len; k += 32) { const double xk = -ry[k] * uy[k]; nn = fma(xk, xk, nn); }
+  nn = warp_sum(nn);
+  const double s0 = uy[0], r0 = ry[0];
+  const double v1 = -r0 * s0;
+  __syncwarp();  // every lane holds s0 before lane 0 may overwrite uy[0]
+  if (len == 1) {
+    if (lane == 0) uy[0] = fmax(v1, 0.0) / r0 + s0;
+    return;
+  }
+  const double sn = len > 2 ? sqrt(nn) : fabs(-ry[1] * uy[1]);
+  if (sn <= v1) {  // x in K: Pi(x) = x, u = -s + s = x / r + s
+    for (int k = lane; k < len; k += 32) { const double sk = uy[k]; uy[k] = (-ry[k] * sk) / ry[k] + sk; }
+    return;
+  }
+  if (sn <= -v1) return;  // Pi(x) = 0: u = s
+  const double alpha = (sn + v1) / 2.0, sc = alpha / sn;
+  for (int k = 1 + lane; k < len; k += 32) { const double sk = uy[k]; uy[k] = ((-ry[k] * sk) * sc) / ry[k] + sk; }
+  if (lane == 0) uy[0] = alpha / r0 + s0;
+}
+
+// One positive-semidefinite cone of the Moreau step, by one warp (cones.c:991-1148 inside cones.c:1562-1585; replaces
+// dsyevr + dsyrk / zheevr + zherk for the small orders a batch member has).  x = -r s is unpacked into a d x d
+// symmetric matrix in shared memory -- real cone: lower triangle, column-major, off-diagonals scaled by sqrt 2;
+// complex cone of order n (cones.c:1087-1095: per column the real diagonal entry, then (re, im) pairs): the real
+// embedding [[Re, -Im], [Im, Re]] of order d = 2n, whose projection is the embedding of the projection.  Classical
+// two-sided Jacobi with the round-robin ordering -- the d/2 disjoint pairs of a round rotate together: angles from the
+// current matrix, then the column updates of all pairs (matrix and eigenvector matrix), then the row updates --
+// until a sweep finds no off-diagonal entry above 1e-17 ||X||_F; X+ = sum_{lambda_k > 0} lambda_k v_k v_k' is
+// re-packed and u = X+ / r + s.
+struct PsdIdx { int i, j, part; };  // packed index -> entry (i >= j); part: 0 diagonal / real part, 1 imaginary part
+__device__ __forceinline__ PsdIdx psd_index(int k, int n, bool cplx) {
+  int j = 0, rem = k;
+  if (!cplx) {
+    while (rem >= n - j) { rem -= n - j; ++j; }
+    return PsdIdx{j + rem, j, 0};
+  }
+  while (rem >= 2 * (n - j) - 1) { rem -= 2 * (n - j) - 1; ++j; }
+  if (rem == 0) return PsdIdx{j, j, 0};
+  return PsdIdx{j + 1 + ((rem - 1) >> 1), j, (rem - 1) & 1};
+}
+__device__ void psd_moreau_warp(double *uy, const double *ry, int len, bool cplx, double *ws, int lane) {
+  if (len <= 0) return;
+  if (len == 1) {
+    if (lane == 0) { const double s0 = uy[0], r0 = ry[0]; uy[0] = fmax(-r0 * s0, 0.0) / r0 + s0; }
+    return;
+  }
+  const int n = cplx ? (int)(sqrt((double)len) + 0.5) : (int)((sqrt(8.0 * len + 1.0) - 1.0) * 0.5 + 0.5);
+  const int d = cplx ? 2 * n : n;
+  double *A = ws, *V = ws + d * d, *cs = V + d * d;
+  const double isq2 = 0.70710678118654752440, sq2 = 1.41421356237309504880;
+  for (int k = lane; k < d * d; k += 32) { A[k] = 0.0; V[k] = (k / d == k % d) ? 1.0 : 0.0; }
+  __syncwarp();
+  for (int k = lane; k < len; k += 32) {
+    const PsdIdx e = psd_index(k, n, cplx);
+    const double x = -ry[k] * uy[k];
+    const double a = e.i == e.j ? x : x * isq2;
+    if (!cplx) {
+      A[e.i * d + e.j] = a; A[e.j * d + e.i] = a;
+    } else if (e.part == 0) {
+      A[e.i * d + e.j] = a; A[e.j * d + e.i] = a;
+      A[(n + e.i) * d + n + e.j] = a; A[(n + e.j) * d + n + e.i] = a;
+    } else {  // Im H[i][j] = a, Im H[j][i] = -a: top-right block -Im H, bottom-left block Im H
+      A[e.i * d + n + e.j] = -a; A[(n + e.j) * d + e.i] = -a;
+      A[e.j * d + n + e.i] = a; A[(n + e.i) * d + e.j] = a;
+    }
+  }
+  __syncwarp();
+  double fro = 0.0;
+  for (int k = lane; k < d * d; k += 32) fro = fma(A[k], A[k], fro);
+  fro = sqrt(warp_sum(fro));
+  const int de = d + (d & 1), half = de >> 1;
+  const double small = 1e-17 * fro;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double mx = 0.0;
+    for (int r = 0; r < de - 1; ++r) {
+      for (int k = lane; k < half; k += 32) {  // rotation of pair k (Numerical-Recipes form), identity when negligible
+        const int p = k == 0 ? de - 1 : (r + k) % (de - 1), q = k == 0 ? r : (r - k + de - 1) % (de - 1);
+        double c = 1.0, sn = 0.0;
+        if (p < d && q < d) {
+          const double apq = A[p * d + q];
+          mx = fmax(mx, fabs(apq));
+          if (fabs(apq) > small) {
+            const double th = (A[q * d + q] - A[p * d + p]) / (2.0 * apq);
+            const double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+            c = 1.0 / sqrt(t * t + 1.0);
+            sn = t * c;
+          }
+        }
+        cs[2 * k] = c; cs[2 * k + 1] = sn;
+      }
+      __syncwarp();
+      for (int idx = lane; idx < half * d; idx += 32) {  // columns p, q of the matrix and of V
+        const int k = idx / d, i = idx - k * d;
+        const int p = k == 0 ? de - 1 : (r + k) % (de - 1), q = k == 0 ? r : (r - k + de - 1) % (de - 1);
+        const double c = cs[2 * k], sn = cs[2 * k + 1];
+        if (p < d && q < d && sn != 0.0) {
+          const double ap = A[i * d + p], aq = A[i * d + q];
+          A[i * d + p] = c * ap - sn * aq; A[i * d + q] = sn * ap + c * aq;
+          const double vp = V[i * d + p], vq = V[i * d + q];
+          V[i * d + p] = c * vp - sn * vq; V[i * d + q] = sn * vp + c * vq;
+        }
+      }
+      __syncwarp();
+      for (int idx = lane; idx < half * d; idx += 32) {  // rows p, q of the matrix
+        const int k = idx / d, j = idx - k * d;
+        const int p = k == 0 ? de - 1 : (r + k) % (de - 1), q = k == 0 ? r : (r - k + de - 1) % (de - 1);
+        const double c = cs[2 * k], sn = cs[2 * k + 1];
+        if (p < d && q < d && sn != 0.0) {
+          const double ap = A[p * d + j], aq = A[q * d + j];
+          A[p * d + j] = c * ap - sn * aq; A[q * d + j] = sn * ap + c * aq;
+        }
+      }
+      __syncwarp();
+    }
+    mx = warp_max(mx);
+    if (mx <= small) break;  // warp-uniform
+  }
+  for (int k = lane; k < len; k += 32) {
+    const PsdIdx e = psd_index(k, n, cplx);
+    const int ra = e.part ? n + e.i : e.i, rb = e.j;  // Re H+[i][j] = S+[i][j], Im H+[i][j] = S+[n + i][j]
+    double x = 0.0;
+    for (int t = 0; t < d; ++t) {
+      const double lam = A[t * d + t];
+      if (lam > 0.0) x = fma(lam * V[ra * d + t], V[rb * d + t], x);
+    }
+    if (e.i != e.j) x *= sq2;
+    const double sk = uy[k];
+    uy[k] = x / ry[k] + sk;
+  }
+  __syncwarp();  // the workspace is reused by this warp's next cone
+}
 
 // =================================================================== exponential ======
 // Friberg 2021 as restated by the reference (exp_cone.c); v0 = (r0, s0, t0).

@@ -11,7 +11,7 @@
 #include <cooperative_groups.h>
 
 #include "cones.cuh"
-#include "cone3.cuh"
+#include "cone_dev.cuh"
 
 namespace b200 {
 
@@ -135,7 +135,7 @@ k_soc_large(double *__restrict__ x, const double *__restrict__ sv, const double 
   }
 }
 
-// exponential and power cones: device functions in cone3.cuh (shared with the batch engine)
+// exponential and power cones: device functions in cone_dev.cuh (shared with the batch engine)
 __global__ void __launch_bounds__(128)
 k_exp_cones(double *__restrict__ x, const double *__restrict__ sv, const double *__restrict__ r, int ep, int ntot) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntot; i += gridDim.x * blockDim.x) {
