@@ -134,3 +134,22 @@ def test_equilibration_matches_reference_structure():
     assert np.array_equal(D1, D2) and np.array_equal(E1, E2)
     # rows inside one cone share their D entry (cones.c:366-379)
     assert len(set(np.round(D1[5:9], 14))) == 1 and len(set(np.round(D1[9:15], 14))) == 1
+
+
+
+def test_quick_c_test_runner_on_the_reference_cpu_backend():
+    """oracle/ctests_quick_main.c (the table-driven runner tests/test_gpu_boundary.py drives on the GPU through the
+    linsys.h plugin) linked with the reference's OWN CPU indirect backend (make -C oracle ref_ctests_cpu): all 30 of the
+    reference's C test cases pass, the verdict lines are the ones the GPU test parses, the name filter works."""
+    import os, subprocess
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    exe = os.path.join(ref, "run_tests_refcpu_quick")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/run_tests_refcpu_quick not built (make -C oracle ref_ctests_cpu)")
+    cwd = os.path.join(ref, "ctest_data")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600, cwd=cwd)
+    assert r.returncode == 0 and "ALL TESTS PASSED" in r.stdout and "Tests run: 30" in r.stdout, r.stdout[-2000:]
+    assert "sparse-indirect" in r.stdout          # the reference's own backend name (private.c: scs_get_lin_sys_method)
+    r = subprocess.run([exe, "cone"], capture_output=True, text=True, timeout=600, cwd=cwd)
+    ran = [ln.split()[2].rstrip(":") for ln in r.stdout.splitlines() if ln.startswith("[quick runner] ") and ln.endswith(" ok")]
+    assert r.returncode == 0 and ran and all("cone" in name for name in ran) and "Tests run: %d" % len(ran) in r.stdout
