@@ -327,9 +327,11 @@ def cpu_baseline_sample(ips):
     r = reference_window(data, cone, ips, steps=1, warmup=0, budget_s=60.0)
     return dict(value=r["value"], unit="iters/s", cores=r["cores"], kind="port" if r["port"] else "reference",
                 sample="%s on a 1/16-scale instance of the workload (n=%d, m=%d, nnz(A)=%d): iterations [%d, %d) of one "
-                       "cold-start solve by difference of two solve times (setup and g solve cancel); the per-iteration "
-                       "cost is linear in nnz, so the full-size rate is ~1/16 of this.  The full-size figure is what "
-                       "`bench.py --impl reference` prints"
+                       "cold-start solve by difference of two solve times (setup and g solve cancel).  The per-iteration "
+                       "work is linear in nnz, so 1/16 of this is an UPPER bound on the full-size rate: measured at full "
+                       "size (`bench.py --impl reference`, profiles/r2n_bench_reference.json) the reference does 0.73 "
+                       "it/s, about half the scaled figure, because its working set then leaves the host's last-level "
+                       "cache.  The full-size figure is what `bench.py --impl reference` prints"
                        % (r["kind"], data["A"].shape[1], data["A"].shape[0], data["A"].nnz, r["window"][0], r["window"][1]),
                 value_scaled_to_full_workload=r["value"] * scale)
 
